@@ -1,0 +1,11 @@
+"""B200-native (sm_100a) render + score hot path for active perception with NeRFs.
+
+A drop-in for the reference's nerfacc ops, NGP radiance field, test-mode renderers and
+predictive-information scorer; all device work is hand-written CUDA behind the C-ABI library
+``libapnerf.so`` (include/apnerf.h).  There is no CPU or PyTorch fallback.
+"""
+from . import _lib, nerfacc, radiance_fields  # noqa: F401
+from .nerfacc import OccGridEstimator  # noqa: F401
+from .radiance_fields import NGPRadianceField  # noqa: F401
+
+__all__ = ["nerfacc", "radiance_fields", "OccGridEstimator", "NGPRadianceField", "_lib"]

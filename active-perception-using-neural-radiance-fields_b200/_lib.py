@@ -1,0 +1,116 @@
+"""ctypes binding of the in-tree C-ABI library ``libapnerf.so`` (include/apnerf.h).
+
+The prototypes are parsed from the header, so the header is the single source of truth for
+the boundary.  There is NO CPU fallback: if the library is missing or a call fails, the
+product path raises (RuntimeError), exactly like the reference's TORCH_CHECKs.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libapnerf.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "apnerf.h")
+
+_CTYPES = {
+    "int": ctypes.c_int,
+    "long long": ctypes.c_longlong,
+    "float": ctypes.c_float,
+    "int64_t": ctypes.c_int64,
+    "uint64_t": ctypes.c_uint64,
+}
+
+
+def parse_header(path: str = HEADER_PATH):
+    """Return {name: (restype, [argtypes])} for every prototype declared in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = {}
+    for m in re.finditer(r"(?:^|\n)\s*(const char\*|int|long long|void)\s+(apnerf_\w+)\s*\(([^;{]*?)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        argtypes = []
+        args = " ".join(args.split())
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    ty = a.rsplit(" ", 1)[0].replace("const ", "").strip()
+                    argtypes.append(_CTYPES[ty])
+        restype = {"const char*": ctypes.c_char_p, "int": ctypes.c_int, "long long": ctypes.c_longlong,
+                   "void": None}[ret]
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class _Lib:
+    def __init__(self):
+        self._dll = None
+        self._protos = None
+
+    def _load(self):
+        if self._dll is not None:
+            return
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA kernels first (python __graft_entry__.py build); "
+                "this package has no CPU or PyTorch fallback.")
+        dll = ctypes.CDLL(LIB_PATH)
+        protos = parse_header()
+        for name, (restype, argtypes) in protos.items():
+            fn = getattr(dll, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        self._dll, self._protos = dll, protos
+
+    def symbols(self):
+        self._load()
+        return sorted(self._protos)
+
+    def last_error(self) -> str:
+        self._load()
+        return (self._dll.apnerf_last_error() or b"").decode()
+
+    def raw(self, name):
+        self._load()
+        return getattr(self._dll, name)
+
+    def call(self, name, *args):
+        """Call an int-returning entry point; tensors are passed as device pointers, the
+        current CUDA stream is appended automatically when the prototype ends with `stream`."""
+        self._load()
+        fn = getattr(self._dll, name)
+        conv = []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if not a.is_cuda:
+                    raise RuntimeError(f"{name}: expected a CUDA tensor, got {a.device}")
+                if not a.is_contiguous():
+                    raise RuntimeError(f"{name}: tensor arguments must be contiguous")
+                conv.append(ctypes.c_void_p(a.data_ptr()))
+            elif a is None:
+                conv.append(ctypes.c_void_p(0))
+            else:
+                conv.append(a)
+        if len(conv) == len(fn.argtypes) - 1:
+            conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = fn(*conv)
+        if rc != 0:
+            raise RuntimeError(f"{name} failed (code {rc}): {self.last_error()}")
+
+
+LIB = _Lib()
+call = LIB.call
+
+
+def require_cuda(*tensors):
+    """The product has no CPU path: refuse anything that is not a CUDA tensor."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(f"apnerf ops need CUDA tensors (got a tensor on {t.device}); there is no CPU fallback")

@@ -1,0 +1,60 @@
+// Shared helpers for the apnerf sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define APNERF_API extern "C" __attribute__((visibility("default")))
+
+// Error plumbing of the C-ABI: every entry point returns 0 or a cudaError_t value and leaves a
+// message for apnerf_last_error().
+void apnerf_set_error(const char* where, cudaError_t e);
+void apnerf_set_error_msg(const char* msg);
+
+#define APNERF_CHECK_LAUNCH(name)                         \
+  do {                                                    \
+    cudaError_t _e = cudaGetLastError();                  \
+    if (_e != cudaSuccess) {                              \
+      apnerf_set_error(name, _e);                         \
+      return (int)_e;                                     \
+    }                                                     \
+  } while (0)
+
+#define APNERF_CUDA(call)                                 \
+  do {                                                    \
+    cudaError_t _e = (call);                              \
+    if (_e != cudaSuccess) {                              \
+      apnerf_set_error(#call, _e);                        \
+      return (int)_e;                                     \
+    }                                                     \
+  } while (0)
+
+#define APNERF_REQUIRE(cond, msg)                         \
+  do {                                                    \
+    if (!(cond)) {                                        \
+      apnerf_set_error_msg(msg);                          \
+      return (int)cudaErrorInvalidValue;                  \
+    }                                                     \
+  } while (0)
+
+static inline int apnerf_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Grid for a grid-stride kernel: enough CTAs to cover n, capped at a multiple of the SM count.
+static inline int grid_for(long long n, int threads, int ctas_per_sm) {
+  long long need = (n + threads - 1) / threads;
+  long long cap = (long long)apnerf_num_sms() * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}

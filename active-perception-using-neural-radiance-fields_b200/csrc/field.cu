@@ -1,0 +1,108 @@
+// C-ABI entry points of the radiance field (kernels 2 + 3): the fused hash-grid + MLP forward
+// and a stand-alone hash-grid encode used for the bit-exact cell-index parity tests.
+// Replaces tcnn.NetworkWithInputEncoding / tcnn.Network / tcnn.Encoding as used by
+// NGPRadianceField (perception/models/radiance_fields/ngp.py:107-238).
+#include "field_kernel.cuh"
+
+namespace apnerf {
+
+__global__ void __launch_bounds__(256) hashgrid_encode_kernel(long long n, const float* __restrict__ x01,
+                                                              const uint2* __restrict__ table, HashGridMeta meta,
+                                                              __half* __restrict__ out_enc,
+                                                              uint32_t* __restrict__ out_idx) {
+  const long long total = n * meta.n_levels;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)blockDim.x * gridDim.x) {
+    const long long s = t / meta.n_levels;
+    const int l = (int)(t % meta.n_levels);
+    const float x[3] = {x01[3 * s], x01[3 * s + 1], x01[3 * s + 2]};
+    if (out_enc) {
+      const uint2 f = encode_level(meta, l, x, table);
+      *reinterpret_cast<uint2*>(out_enc + s * (meta.n_levels * FEATS) + l * FEATS) = f;
+    }
+    if (out_idx) {
+      uint32_t cell[3];
+      float w[3];
+      level_cell(meta, l, x, cell, w);
+      for (int c = 0; c < 8; ++c) out_idx[(s * meta.n_levels + l) * 8 + c] = corner_index(meta, l, cell, c);
+    }
+  }
+}
+
+static int fill_meta(HashGridMeta& m, int n_levels, const uint32_t* meta_host) {
+  if (n_levels < 1 || n_levels > MAX_LEVELS) return 1;
+  m.n_levels = n_levels;
+  for (int l = 0; l < MAX_LEVELS; ++l) {
+    if (l < n_levels) {
+      uint32_t bits = meta_host[5 * l + 0];
+      float sc;
+      memcpy(&sc, &bits, 4);
+      m.scale[l] = sc;
+      m.res[l] = meta_host[5 * l + 1];
+      m.size[l] = meta_host[5 * l + 2];
+      m.offset[l] = meta_host[5 * l + 3];
+      m.hashed[l] = meta_host[5 * l + 4];
+      if (m.hashed[l] && (m.size[l] & (m.size[l] - 1))) return 2;
+    } else {
+      m.scale[l] = 0.f, m.res[l] = 1, m.size[l] = 1, m.offset[l] = 0, m.hashed[l] = 0;
+    }
+  }
+  return 0;
+}
+
+}  // namespace apnerf
+
+using namespace apnerf;
+
+// meta_host: HOST array [n_levels][5] u32 = {scale (f32 bits), resolution, size, offset, hashed}.
+APNERF_API int apnerf_hashgrid_encode(long long n, const float* x01, int n_levels, const uint32_t* meta_host,
+                                      const void* table, void* out_enc, uint32_t* out_idx, void* stream) {
+  if (n == 0) return 0;
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "hashgrid_encode: bad level table");
+  hashgrid_encode_kernel<<<grid_for(n * n_levels, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      n, x01, (const uint2*)table, m, (__half*)out_enc, out_idx);
+  APNERF_CHECK_LAUNCH("hashgrid_encode_kernel");
+  return 0;
+}
+
+// Fused field query.  Exactly one of {positions(+directions)} / {ray_idx, t_starts, t_ends,
+// rays_o, rays_d} describes the sample points.  n_dev (optional, device int32) overrides n.
+// Outputs: density [n]; rgb / sem element (i, c) at base[c * ch_stride + i * row_stride].
+APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* positions, const float* directions,
+                                    const int* ray_idx, const float* t_starts, const float* t_ends,
+                                    const float* rays_o, const float* rays_d, const float* aabb_host,
+                                    int n_levels, const uint32_t* meta_host, const void* table,
+                                    const void* weights, float* density, float* rgb, long long rgb_row,
+                                    long long rgb_ch, float* sem, long long sem_row, long long sem_ch, int n_sem,
+                                    void* feat, int density_only, long long max_tiles, void* stream) {
+  if (n == 0 && n_dev == nullptr) return 0;
+  APNERF_REQUIRE(positions != nullptr || ray_idx != nullptr, "field_forward: no sample points given");
+  APNERF_REQUIRE(density_only || positions == nullptr || directions != nullptr, "field_forward: directions missing");
+  APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward: at most 32 semantic classes");
+  static bool attr_set = false;
+  if (!attr_set) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    attr_set = true;
+  }
+  FieldIO io;
+  io.n = n, io.n_dev = n_dev, io.positions = positions, io.directions = directions, io.ray_idx = ray_idx;
+  io.t_starts = t_starts, io.t_ends = t_ends, io.rays_o = rays_o, io.rays_d = rays_d;
+  io.table = (const uint2*)table, io.weights = (const uint4*)weights;
+  io.density = density, io.rgb = rgb, io.rgb_row = rgb_row, io.rgb_ch = rgb_ch;
+  io.sem = sem, io.sem_row = sem_row, io.sem_ch = sem_ch, io.feat = (__half*)feat, io.n_sem = sem ? n_sem : 0;
+  io.density_only = density_only;
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward: bad level table");
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
+  long long tiles = n_dev ? max_tiles : (n + TILE_M - 1) / TILE_M;
+  if (tiles < 1) tiles = 1;
+  const int sms = apnerf_num_sms();
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  field_forward_kernel<<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  APNERF_CHECK_LAUNCH("field_forward_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_field_weight_bytes(void) { return W_BYTES; }

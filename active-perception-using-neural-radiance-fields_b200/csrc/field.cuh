@@ -1,0 +1,142 @@
+// Radiance-field device code shared by field.cu (drop-in query kernels) and render.cu (the
+// fused test-mode renderer): multiresolution hash-grid addressing / interpolation (kernel 2),
+// SH-4 direction encoding, and the layout constants of the tcgen05 MLP (kernel 3).
+//
+// Specification: tiny-cuda-nn's HashGrid / SphericalHarmonics / FullyFusedMLP as configured by
+// the reference at perception/models/radiance_fields/ngp.py:107-169.
+// tiny-cuda-nn is an external, unpinned dependency that is absent from the reference tree, so
+// parity is checked against the CPU restatement in oracle/ ("parity unpinned").
+#pragma once
+#include "common.cuh"
+
+namespace apnerf {
+
+constexpr int MAX_LEVELS = 16;
+constexpr int FEATS = 4;  // features per level (ngp.py:128)
+
+struct HashGridMeta {  // by-value kernel parameter (constant bank)
+  float scale[MAX_LEVELS];
+  uint32_t res[MAX_LEVELS];
+  uint32_t size[MAX_LEVELS];    // entries in the level
+  uint32_t offset[MAX_LEVELS];  // first entry of the level in the table
+  uint32_t hashed[MAX_LEVELS];  // 1: spatial hash, 0: dense (x fastest)
+  int n_levels;
+};
+
+struct FieldConst {
+  float aabb[6];
+};
+
+// x in aabb-normalised coordinates -> table entry index of corner c (bit a of c = +1 on axis a)
+// and the level's interpolation weights.  Integer math is uint32 with wrap-around, as in tcnn.
+__device__ __forceinline__ void level_cell(const HashGridMeta& m, int l, const float x[3], uint32_t cell[3],
+                                           float w[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float pos = __fmaf_rn(m.scale[l], x[a], 0.5f);
+    const float fl = floorf(pos);
+    cell[a] = (uint32_t)__float2int_rz(fl);
+    w[a] = __fsub_rn(pos, fl);
+  }
+}
+
+__device__ __forceinline__ uint32_t corner_index(const HashGridMeta& m, int l, const uint32_t cell[3], int c) {
+  const uint32_t gx = cell[0] + (c & 1), gy = cell[1] + ((c >> 1) & 1), gz = cell[2] + ((c >> 2) & 1);
+  uint32_t idx;
+  if (m.hashed[l]) {
+    idx = gx ^ (gy * 2654435761u) ^ (gz * 805459861u);
+    idx &= (m.size[l] - 1u);  // hashed levels have a power-of-two size (2^log2_hashmap_size)
+  } else {
+    const uint32_t r = m.res[l];
+    idx = gx + gy * r + gz * r * r;
+    if (idx >= m.size[l]) idx %= m.size[l];  // only for points outside the unit cube
+  }
+  return m.offset[l] + idx;
+}
+
+__device__ __forceinline__ float corner_weight(const float w[3], int c) {
+  float wt = (c & 1) ? w[0] : __fsub_rn(1.0f, w[0]);
+  wt = __fmul_rn(wt, (c & 2) ? w[1] : __fsub_rn(1.0f, w[1]));
+  wt = __fmul_rn(wt, (c & 4) ? w[2] : __fsub_rn(1.0f, w[2]));
+  return wt;
+}
+
+// Interpolate one level: 8 x 8-byte gathers (read-only path), fp32 blend in corner order,
+// result rounded to fp16 and packed as 2 x u32 (features 0,1 | 2,3).
+__device__ __forceinline__ uint2 encode_level(const HashGridMeta& m, int l, const float x[3],
+                                              const uint2* __restrict__ table) {
+  uint32_t cell[3];
+  float w[3];
+  level_cell(m, l, x, cell, w);
+  uint2 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __ldg(table + corner_index(m, l, cell, c));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float wt = corner_weight(w, c);
+    const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&v[c].x));
+    const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&v[c].y));
+    acc[0] = __fmaf_rn(wt, f01.x, acc[0]);
+    acc[1] = __fmaf_rn(wt, f01.y, acc[1]);
+    acc[2] = __fmaf_rn(wt, f23.x, acc[2]);
+    acc[3] = __fmaf_rn(wt, f23.y, acc[3]);
+  }
+  const __half2 h01 = __floats2half2_rn(acc[0], acc[1]);
+  const __half2 h23 = __floats2half2_rn(acc[2], acc[3]);
+  uint2 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&h01);
+  o.y = *reinterpret_cast<const uint32_t*>(&h23);
+  return o;
+}
+
+// Real spherical harmonics, degree 4 (16 coefficients), evaluated on d itself: the reference
+// feeds (d + 1) / 2 (ngp.py:205) and tcnn maps it back with 2u - 1.  Every product / sum is
+// individually rounded (the file is compiled with --fmad=false).
+__device__ __forceinline__ void sh4(const float d[3], float o[16]) {
+  const float u0 = (d[0] + 1.0f) / 2.0f, u1 = (d[1] + 1.0f) / 2.0f, u2 = (d[2] + 1.0f) / 2.0f;
+  const float x = u0 * 2.0f - 1.0f, y = u1 * 2.0f - 1.0f, z = u2 * 2.0f - 1.0f;
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = (0.59004358992664352f * y) * (-3.0f * x2 + y2);
+  o[10] = (2.8906114426405538f * xy) * z;
+  o[11] = (0.45704579946446572f * y) * (1.0f - 5.0f * z2);
+  o[12] = (0.3731763325901154f * z) * (5.0f * z2 - 3.0f);
+  o[13] = (0.45704579946446572f * x) * (1.0f - 5.0f * z2);
+  o[14] = (1.4453057213202769f * z) * (x2 - y2);
+  o[15] = (0.59004358992664352f * x) * (-x2 + 3.0f * y2);
+}
+
+// ---- MLP geometry (ngp.py:134-169 with neurons = 128, layers = 2, geo_feat_dim = 15) -------
+// Matrices are stored [out, in] (K-major for the MMA's B operand) as fp16 in the UMMA
+// "interleaved" no-swizzle layout: element (n, k) at byte (k / 8) * (N * 16) + n * 16 + (k % 8) * 2.
+constexpr int TILE_M = 128;                  // samples per tile = MMA M = TMEM lanes
+constexpr int ENC_DIM = MAX_LEVELS * FEATS;  // 64
+constexpr int HID = 128;                     // base MLP width
+constexpr int BASE_OUT = 16;                 // 1 density + 15 geo features
+constexpr int HEAD_IN = 32;                  // 16 SH + 15 geo + 1.0 pad
+constexpr int SEM_IN = 16;                   // 15 geo + 1.0 pad
+constexpr int HID2 = 64;                     // head / semantic MLP width
+constexpr int HEAD_OUT = 16;                 // 3 rgb padded to 16
+constexpr int SEM_OUT = 32;                  // <= 32 classes padded to 32
+
+constexpr int W1_OFF = 0;                                // [128 x 64]
+constexpr int W2_OFF = W1_OFF + HID * ENC_DIM * 2;       // [128 x 128]
+constexpr int W3_OFF = W2_OFF + HID * HID * 2;           // [16 x 128]
+constexpr int WH1_OFF = W3_OFF + BASE_OUT * HID * 2;     // [64 x 32]
+constexpr int WH2_OFF = WH1_OFF + HID2 * HEAD_IN * 2;    // [64 x 64]
+constexpr int WH3_OFF = WH2_OFF + HID2 * HID2 * 2;       // [16 x 64]
+constexpr int WS1_OFF = WH3_OFF + HEAD_OUT * HID2 * 2;   // [64 x 16]
+constexpr int WS2_OFF = WS1_OFF + HID2 * SEM_IN * 2;     // [64 x 64]
+constexpr int WS3_OFF = WS2_OFF + HID2 * HID2 * 2;       // [32 x 64]
+constexpr int W_BYTES = WS3_OFF + SEM_OUT * HID2 * 2;    // 81920
+
+}  // namespace apnerf

@@ -1,0 +1,163 @@
+// Occupancy-grid ray marcher (kernel 1).  One thread walks one ray; a warp holds 32
+// neighbouring rays of the same image so the DDA stays coherent.
+//
+// Replaces the reference's traverse_grids_kernel (perception/nerfacc/nerfacc/cuda/csrc/grid.cu:68-282,
+// helpers include/utils_grid.cuh:58-142).  The march is a serial fp32 recurrence, so bit-exact
+// parity fixes every rounding: each operation below is an explicit round-to-nearest intrinsic
+// (never contracted by the compiler), and fused multiply-adds appear exactly where the
+// reference build has an FFMA.
+#pragma once
+#include "common.cuh"
+
+namespace apnerf {
+
+struct GridView {
+  const uint8_t* binaries;  // [n_grids, rx, ry, rz] bool
+  const float* aabbs;       // [n_grids, 6]
+  int n_grids;
+  int rx, ry, rz;
+};
+
+__device__ __forceinline__ float calc_dt(float t, float cone, float dt_min) {
+  // grid.cu:23-28 : clamp(t * cone, dt_min, 1e10) = fmaxf(dt_min, fminf(t * cone, 1e10))
+  return fmaxf(dt_min, fminf(__fmul_rn(t, cone), 1e10f));
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(v, hi)); }
+
+// Slab test, include/utils_grid.cuh:10-55.  inv = 1/d (rcp.rn).
+__device__ __forceinline__ bool ray_aabb(const float o[3], const float inv[3], float rtmin, float rtmax,
+                                         const float* __restrict__ ab, float& tmin, float& tmax) {
+  float a, b;
+  if (inv[0] >= 0) { tmin = __fmul_rn(__fsub_rn(ab[0], o[0]), inv[0]); tmax = __fmul_rn(__fsub_rn(ab[3], o[0]), inv[0]); }
+  else             { tmin = __fmul_rn(__fsub_rn(ab[3], o[0]), inv[0]); tmax = __fmul_rn(__fsub_rn(ab[0], o[0]), inv[0]); }
+  if (inv[1] >= 0) { a = __fmul_rn(__fsub_rn(ab[1], o[1]), inv[1]); b = __fmul_rn(__fsub_rn(ab[4], o[1]), inv[1]); }
+  else             { a = __fmul_rn(__fsub_rn(ab[4], o[1]), inv[1]); b = __fmul_rn(__fsub_rn(ab[1], o[1]), inv[1]); }
+  if (tmin > b || a > tmax) return false;
+  if (a > tmin) tmin = a;
+  if (b < tmax) tmax = b;
+  if (inv[2] >= 0) { a = __fmul_rn(__fsub_rn(ab[2], o[2]), inv[2]); b = __fmul_rn(__fsub_rn(ab[5], o[2]), inv[2]); }
+  else             { a = __fmul_rn(__fsub_rn(ab[5], o[2]), inv[2]); b = __fmul_rn(__fsub_rn(ab[2], o[2]), inv[2]); }
+  if (tmin > b || a > tmax) return false;
+  if (a > tmin) tmin = a;
+  if (b < tmax) tmax = b;
+  if (tmax <= 0) return false;
+  tmin = fmaxf(tmin, rtmin);
+  tmax = fminf(tmax, rtmax);
+  return true;
+}
+
+// March one ray.  `sink(t_last, t_next, continuous)` is called once per emitted sample, in
+// order; it returns nothing (counting is done here).  `limit` <= 0 means unlimited.
+// Returns the number of samples; `n_intervals` gets the number of interval edges
+// (#samples + #runs) and `t_term` the terminate plane (grid.cu:274-280).
+template <class Sink>
+__device__ __forceinline__ int march_ray(const GridView& g, const float o[3], const float d[3],
+                                         float near_plane, float far_plane,
+                                         const uint8_t* __restrict__ hits,        // [n_grids] of this ray
+                                         const float* __restrict__ t_sorted,      // [2*n_grids]
+                                         const int64_t* __restrict__ t_indices,   // [2*n_grids] or nullptr (identity)
+                                         float step_size, float cone_angle, int limit, Sink& sink,
+                                         int& n_intervals, float& t_term) {
+  const float eps = 1e-6f;
+  const float inv[3] = {__frcp_rn(d[0]), __frcp_rn(d[1]), __frcp_rn(d[2])};
+  int n_samples = 0;
+  n_intervals = 0;
+  float t_last = near_plane;
+  bool continuous = false;
+  const int n_grids = g.n_grids;
+  for (int i = 0; i < n_grids * 2 - 1; ++i) {  // grid.cu:129
+    const int64_t ti = t_indices ? t_indices[i] : (int64_t)i;
+    const bool is_entering = ti < n_grids;
+    int level = (int)(ti % n_grids);
+    if (!hits[level]) continue;
+    if (!is_entering) {
+      const int64_t tn = t_indices ? t_indices[i + 1] : (int64_t)(i + 1);
+      if (tn < n_grids) continue;
+      level = (int)(tn % n_grids);
+      if (!hits[level]) continue;
+    }
+    const float this_tmin = fmaxf(t_sorted[i], near_plane);
+    const float this_tmax = fminf(t_sorted[i + 1], far_plane);
+    if (this_tmin >= this_tmax) continue;
+
+    if (!continuous) {  // grid.cu:153-163
+      if (step_size <= 0.0f) {
+        t_last = this_tmin;
+      } else {
+        const float dt = calc_dt(t_last, cone_angle, step_size);
+        while (__fmaf_rn(dt, 0.5f, t_last) < this_tmin) t_last = __fadd_rn(t_last, dt);
+      }
+    }
+
+    // setup_traversal, include/utils_grid.cuh:58-114
+    const float* __restrict__ ab = g.aabbs + level * 6;
+    const int resv[3] = {g.rx, g.ry, g.rz};
+    float tdist[3], delta[3];
+    int cur[3], stp[3], ovf[3];
+    const float ts = __fadd_rn(this_tmin, eps), te = __fsub_rn(this_tmax, eps);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float fres = (float)resv[a];
+      const float ext = __fsub_rn(ab[3 + a], ab[a]);
+      const float voxel = __fdiv_rn(ext, fres);
+      const float ray_start = __fmaf_rn(d[a], ts, o[a]);
+      const float ray_end = __fmaf_rn(d[a], te, o[a]);
+      cur[a] = clampi(__float2int_rz(__fmul_rn(__fdiv_rn(__fsub_rn(ray_start, ab[a]), ext), fres)), 0, resv[a] - 1);
+      const int fin = clampi(__float2int_rz(__fmul_rn(__fdiv_rn(__fsub_rn(ray_end, ab[a]), ext), fres)), 0, resv[a] - 1);
+      const int start_index = cur[a] + (d[a] > 0.0f ? 1 : 0);
+      const float inner = __fmaf_rn((float)start_index, voxel, -ray_start);
+      const float tm = __fmaf_rn(__fadd_rn(ab[a], inner), inv[a], this_tmin);
+      const float sf = (d[a] == 0.0f) ? 0.0f : (d[a] > 0.0f ? 1.0f : -1.0f);
+      tdist[a] = (d[a] == 0.0f) ? this_tmax : tm;
+      stp[a] = (int)sf;
+      delta[a] = (d[a] == 0.0f) ? this_tmax : __fmul_rn(__fmul_rn(voxel, inv[a]), sf);
+      ovf[a] = fin + stp[a];
+    }
+    const int64_t level_base = (int64_t)level * g.rx * g.ry * g.rz;
+
+    while (limit <= 0 || n_samples < limit) {  // grid.cu:184
+      float t_traverse = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
+      const int64_t cell_id = (int64_t)(cur[0] * g.ry * g.rz + cur[1] * g.rz + cur[2]) + level_base;
+      if (!g.binaries[cell_id]) {
+        if (step_size <= 0.0f) {
+          t_last = t_traverse;
+        } else {
+          const float dt = calc_dt(t_last, cone_angle, step_size);
+          while (__fmaf_rn(dt, 0.5f, t_last) < t_traverse) t_last = __fadd_rn(t_last, dt);
+        }
+        continuous = false;
+      } else {
+        while (limit <= 0 || n_samples < limit) {  // grid.cu:208
+          float t_next;
+          if (step_size <= 0.0f) {
+            t_next = t_traverse;
+          } else {
+            const float dt = calc_dt(t_last, cone_angle, step_size);
+            if (__fmaf_rn(dt, 0.5f, t_last) >= t_traverse) break;
+            t_next = __fadd_rn(t_last, dt);
+          }
+          sink(t_last, t_next, continuous, n_samples, n_intervals);
+          n_intervals += continuous ? 1 : 2;
+          n_samples++;
+          continuous = true;
+          t_last = t_next;
+          if (t_next >= t_traverse) break;
+        }
+      }
+      // single_traversal, include/utils_grid.cuh:116-142
+      int a;
+      if ((tdist[0] < tdist[1]) && (tdist[0] < tdist[2])) a = 0;
+      else if (tdist[1] < tdist[2]) a = 1;
+      else a = 2;
+      // (dynamic indexing on 3-element register arrays: resolved with selects)
+      if (a == 0) { cur[0] += stp[0]; tdist[0] = __fadd_rn(tdist[0], delta[0]); if (cur[0] == ovf[0]) break; }
+      else if (a == 1) { cur[1] += stp[1]; tdist[1] = __fadd_rn(tdist[1], delta[1]); if (cur[1] == ovf[1]) break; }
+      else { cur[2] += stp[2]; tdist[2] = __fadd_rn(tdist[2], delta[2]); if (cur[2] == ovf[2]) break; }
+    }
+  }
+  t_term = t_last;
+  return n_samples;
+}
+
+}  // namespace apnerf

@@ -1,0 +1,235 @@
+"""NGPRadianceField without tiny-cuda-nn: same constructor, methods, attributes and
+``state_dict`` keys as the reference (perception/models/radiance_fields/ngp.py:69-238), with the
+hash grid + three MLPs evaluated by ONE fused sm_100a kernel (csrc/field_kernel.cuh).
+
+Parameter layout (tcnn-compatible, flat fp32, so reference checkpoints load):
+  mlp_base.params = [W1 (neurons x 64) | W2 (neurons x neurons) ... | W_out (16 x neurons) | grid (entries x 4)]
+  mlp_head.params = [64 x 32 | 64 x 64 | 16 x 64]      (inputs padded to 32 with 1.0, outputs 3 -> 16)
+  mlp_sem.params  = [64 x 16 | 64 x 64 | 32 x 64]      (inputs padded to 16 with 1.0, outputs C -> 32)
+  direction_encoding.params = []  (SH has no parameters; kept so every named parameter exists)
+All matrices are row-major [out, in], no biases.
+"""
+from typing import Callable, List, Union
+
+import numpy as np
+import torch
+
+from .._lib import LIB, call, require_cuda
+
+
+class _TruncExp(torch.autograd.Function):
+    """exp forward, gradient clamped at exp(15) (ngp.py:23-39)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float()
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(torch.clamp(x, max=15))
+
+
+trunc_exp = _TruncExp.apply
+
+
+def hashgrid_levels(n_levels, base_resolution, max_resolution, log2_hashmap_size):
+    """[n_levels, 5] uint32 rows {scale (f32 bits), resolution, entries, first entry, hashed} and
+    the total number of table entries (tcnn GridEncoding; ngp.py:103-105,123-133)."""
+    per_level_scale = np.exp((np.log(max_resolution) - np.log(base_resolution)) / (n_levels - 1))
+    meta = np.zeros((n_levels, 5), dtype=np.uint32)
+    offset = 0
+    for lvl in range(n_levels):
+        scale = np.exp2(lvl * np.log2(per_level_scale)) * base_resolution - 1.0
+        res = int(np.ceil(scale)) + 1
+        dense = res ** 3
+        size = min((dense + 7) // 8 * 8, 1 << log2_hashmap_size)
+        meta[lvl] = (np.float32(scale).view(np.uint32), res, size, offset, 1 if size < dense else 0)
+        offset += size
+    return meta, offset
+
+
+class _FlatParams(torch.nn.Module):
+    """Stand-in for a tcnn module: one flat fp32 ``params`` Parameter."""
+
+    def __init__(self, n_params: int, n_output_dims: int = 0):
+        super().__init__()
+        self.params = torch.nn.Parameter(torch.zeros(n_params, dtype=torch.float32))
+        self.n_output_dims = n_output_dims
+
+
+def _pad16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+def _xavier_(flat: torch.Tensor, dims, generator=None):
+    o = 0
+    for n_out, n_in in dims:
+        bound = float(np.sqrt(6.0 / (n_in + n_out)))
+        flat[o:o + n_out * n_in].uniform_(-bound, bound, generator=generator)
+        o += n_out * n_in
+    return o
+
+
+def _umma_pack(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] fp16 -> UMMA K-major no-swizzle image: element (n, k) at (k//8)*(N*8) + n*8 + k%8."""
+    n, k = w.shape
+    return w.reshape(n, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+class NGPRadianceField(torch.nn.Module):
+    """Instant-NGP radiance field with an optional semantic head."""
+
+    def __init__(
+        self,
+        aabb: Union[torch.Tensor, List[float]],
+        num_dim: int = 3,
+        use_viewdirs: bool = True,
+        neurons: int = 128,
+        layers: int = 4,
+        density_activation: Callable = lambda x: trunc_exp(x - 1),
+        unbounded: bool = False,
+        base_resolution: int = 16,
+        max_resolution: int = 4096,
+        geo_feat_dim: int = 15,
+        n_levels: int = 16,
+        log2_hashmap_size: int = 19,
+        num_semantic_classes: int = 0,
+    ) -> None:
+        super().__init__()
+        if not isinstance(aabb, torch.Tensor):
+            aabb = torch.tensor(aabb, dtype=torch.float32)
+        self.register_buffer("aabb", aabb)
+        self.num_dim = num_dim
+        self.use_viewdirs = use_viewdirs
+        self.density_activation = density_activation
+        self.unbounded = unbounded
+        self.base_resolution = base_resolution
+        self.max_resolution = max_resolution
+        self.geo_feat_dim = geo_feat_dim
+        self.n_levels = n_levels
+        self.log2_hashmap_size = log2_hashmap_size
+        self.num_semantic_classes = num_semantic_classes
+        self.neurons = neurons
+        self.layers = layers
+        # what the sm_100a kernel is built for (the pipeline's configuration, config_*.yaml:17-18)
+        if (num_dim != 3 or not use_viewdirs or unbounded or neurons != 128 or layers != 2 or geo_feat_dim != 15
+                or n_levels > 16 or num_semantic_classes > 32):
+            raise NotImplementedError(
+                "the fused sm_100a field kernel supports num_dim=3, use_viewdirs=True, unbounded=False, "
+                "neurons=128, layers=2, geo_feat_dim=15, n_levels<=16, num_semantic_classes<=32 "
+                f"(got neurons={neurons}, layers={layers}, geo_feat_dim={geo_feat_dim}, n_levels={n_levels}, "
+                f"num_semantic_classes={num_semantic_classes}, unbounded={unbounded})")
+
+        self._meta, self._n_entries = hashgrid_levels(n_levels, base_resolution, max_resolution, log2_hashmap_size)
+        enc_dim = 64  # the kernel's A tile is 64 wide; levels beyond n_levels read as zeros
+        self._base_dims = [(neurons, enc_dim)] + [(neurons, neurons)] * (layers - 1) + [(16, neurons)]
+        self._head_dims = [(neurons // 2, 32), (neurons // 2, neurons // 2), (16, neurons // 2)]
+        self._sem_dims = [(neurons // 2, 16), (neurons // 2, neurons // 2), (32, neurons // 2)]
+        n_base_w = sum(a * b for a, b in self._base_dims)
+
+        self.direction_encoding = _FlatParams(0, n_output_dims=16)
+        self.mlp_base = _FlatParams(n_base_w + self._n_entries * 4, n_output_dims=1 + geo_feat_dim)
+        self.mlp_head = _FlatParams(sum(a * b for a, b in self._head_dims), n_output_dims=3)
+        if num_semantic_classes > 0:
+            self.mlp_sem = _FlatParams(sum(a * b for a, b in self._sem_dims), n_output_dims=num_semantic_classes)
+        self._n_base_w = n_base_w
+        self._cache = None
+        self._cache_key = None
+        self.reset_parameters()
+
+    # -- initialisation: tcnn defaults (Xavier-uniform MLPs, grid U(-1e-4, 1e-4)) --
+    @torch.no_grad()
+    def reset_parameters(self, grid_range: float = 1e-4, generator=None):
+        o = _xavier_(self.mlp_base.params, self._base_dims, generator)
+        self.mlp_base.params[o:].uniform_(-grid_range, grid_range, generator=generator)
+        _xavier_(self.mlp_head.params, self._head_dims, generator)
+        if self.num_semantic_classes > 0:
+            _xavier_(self.mlp_sem.params, self._sem_dims, generator)
+
+    # -- fp16 inference image of the parameters (rebuilt when a parameter changes) --
+    def _packed(self):
+        ps = [self.mlp_base.params, self.mlp_head.params]
+        if self.num_semantic_classes > 0:
+            ps.append(self.mlp_sem.params)
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+        if self._cache is not None and key == self._cache_key:
+            return self._cache
+        with torch.no_grad():
+            dev = self.mlp_base.params.device
+
+            def mats(flat, dims):
+                out, o = [], 0
+                for n_out, n_in in dims:
+                    out.append(_umma_pack(flat[o:o + n_out * n_in].reshape(n_out, n_in).to(torch.float16)))
+                    o += n_out * n_in
+                return out
+
+            blobs = mats(self.mlp_base.params, self._base_dims) + mats(self.mlp_head.params, self._head_dims)
+            if self.num_semantic_classes > 0:
+                blobs += mats(self.mlp_sem.params, self._sem_dims)
+            else:
+                blobs += [torch.zeros(a * b, dtype=torch.float16, device=dev) for a, b in self._sem_dims]
+            weights = torch.cat(blobs).contiguous()
+            assert weights.numel() * 2 == int(LIB.raw("apnerf_field_weight_bytes")())
+            table = self.mlp_base.params[self._n_base_w:].to(torch.float16).contiguous()
+            self._cache = (weights, table)
+            self._cache_key = key
+        return self._cache
+
+    def _run(self, positions, directions, density_only, return_feat=False):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError(
+                "NGPRadianceField: the backward pass of the fused field kernel is not built yet; call under "
+                "torch.no_grad() / .eval() (there is no tcnn or PyTorch fallback)")
+        require_cuda(positions, directions, self.mlp_base.params)
+        weights, table = self._packed()
+        pos = positions.reshape(-1, 3).to(torch.float32).contiguous()
+        n = pos.shape[0]
+        dev = pos.device
+        density = torch.empty(n, device=dev, dtype=torch.float32)
+        aabb_host = (np.asarray(self.aabb.detach().cpu().numpy(), dtype=np.float32)
+                     if getattr(self, "_aabb_host", None) is None else self._aabb_host)
+        self._aabb_host = aabb_host
+        feat = torch.empty((n, 15), device=dev, dtype=torch.float16) if return_feat else None
+        rgb = sem = dirs = None
+        C = self.num_semantic_classes
+        if not density_only:
+            dirs = directions.reshape(-1, 3).to(torch.float32).contiguous()
+            rgb = torch.empty((n, 3), device=dev, dtype=torch.float32)
+            sem = torch.empty((n, C), device=dev, dtype=torch.float32) if C > 0 else None
+        if n:
+            import ctypes
+            with torch.cuda.device(dev):
+                call("apnerf_field_forward", n, None, pos, dirs, None, None, None, None, None,
+                     aabb_host.ctypes.data_as(ctypes.c_void_p), self.n_levels,
+                     self._meta.ctypes.data_as(ctypes.c_void_p), table, weights, density,
+                     rgb, 3, 1, sem, C, 1, C, feat, 1 if density_only else 0, 0)
+        return density, rgb, sem, feat
+
+    def _apply(self, fn, *a, **k):
+        self._cache = None
+        self._aabb_host = None
+        return super()._apply(fn, *a, **k)
+
+    def query_density(self, x, return_feat: bool = False):
+        """ngp.py:171-200: density [..., 1] (and the 15 geo features, upcast like ``.to(x)``)."""
+        density, _, _, feat = self._run(x, None, True, return_feat)
+        density = density.reshape(list(x.shape[:-1]) + [1])
+        if return_feat:
+            return density, feat.to(x.dtype).reshape(list(x.shape[:-1]) + [self.geo_feat_dim])
+        return density
+
+    def forward(self, positions: torch.Tensor, directions: torch.Tensor = None):
+        """ngp.py:222-238: (rgb, density[, sem_logits])."""
+        assert self.use_viewdirs and directions is not None
+        assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
+        density, rgb, sem, _ = self._run(positions, directions, False)
+        lead = list(positions.shape[:-1])
+        rgb = rgb.reshape(lead + [3])
+        density = density.reshape(lead + [1])
+        if self.num_semantic_classes > 0:
+            return rgb, density, sem.reshape(lead + [self.num_semantic_classes])
+        return rgb, density

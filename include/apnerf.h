@@ -1,0 +1,130 @@
+/*
+ * apnerf.h -- C-ABI of libapnerf.so: the B200 (sm_100a) render + score hot path of
+ * grasp-lyrl/Active-Perception-using-Neural-Radiance-Fields.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`; buffers are
+ *     contiguous, caller-owned and caller-sized (nothing is allocated behind the boundary
+ *     except by the apnerf_*_create calls, which say so);
+ *   - bool tensors are 1 byte per element (torch.bool), indices are int64, values float32,
+ *     exactly as in the reference's pybind module (perception/nerfacc/nerfacc/cuda/csrc/nerfacc.cpp:100-129);
+ *   - `stream` is a cudaStream_t (0 = legacy default stream); calls only enqueue work;
+ *   - return value 0 = ok, otherwise a cudaError_t; apnerf_last_error() describes it.  The
+ *     Python host maps non-zero to RuntimeError, as TORCH_CHECK does in the reference
+ *     (csrc/scan.cu:18-26, csrc/grid.cu:345).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef APNERF_H
+#define APNERF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* apnerf_last_error(void);
+int apnerf_abi_version(void);
+
+/* ---- kernel (1): ray / AABB slab test and occupancy-grid traversal ------------------- */
+
+/* nerfacc_cuda.ray_aabb_intersect -- csrc/grid.cu:477-519 (kernel :284-313).
+ * t_mins/t_maxs [n_rays, n_aabbs] f32, hits [n_rays, n_aabbs] bool. */
+int apnerf_ray_aabb_intersect(int n_rays, const float* rays_o, const float* rays_d, int n_aabbs,
+                              const float* aabbs, float near_plane, float far_plane, float miss_value,
+                              float* t_mins, float* t_maxs, uint8_t* hits, void* stream);
+
+/* One launch of the reference's traverse_grids_kernel -- csrc/grid.cu:68-282, launched from
+ * :320-474.  first_pass != 0 only counts (chunk_cnts are written); otherwise segments are
+ * written at chunk_starts[ray].  The iv_* / sm_* groups are the fields of the two
+ * RaySegmentsSpec outputs (csrc/include/data_spec.hpp:6-14); a NULL *_chunk_cnts disables that
+ * group, rays_mask / t_indices / terminate_planes may be NULL (t_indices NULL = identity
+ * order, the single-grid case of perception/models/utils.py:886-892). */
+int apnerf_traverse_grids(int n_rays, const float* rays_o, const float* rays_d, const uint8_t* rays_mask,
+                          int n_grids, int rx, int ry, int rz, const uint8_t* binaries, const float* aabbs,
+                          const uint8_t* hits, const float* t_sorted, const int64_t* t_indices,
+                          const float* near_planes, const float* far_planes, float step_size,
+                          float cone_angle, int traverse_steps_limit, int first_pass,
+                          float* iv_vals, int64_t* iv_ray_indices, uint8_t* iv_is_left, uint8_t* iv_is_right,
+                          const int64_t* iv_chunk_starts, int64_t* iv_chunk_cnts,
+                          float* sm_vals, int64_t* sm_ray_indices, uint8_t* sm_is_valid,
+                          const int64_t* sm_chunk_starts, int64_t* sm_chunk_cnts,
+                          float* terminate_planes, void* stream);
+
+/* chunk_cnts -> chunk_starts (+ device-side total): RaySegmentsSpec::memalloc_data_from_chunk /
+ * compute_chunk_start -- csrc/include/data_spec.hpp:86-106.  scratch: apnerf_scan_scratch_elems(n)
+ * int64 elements. */
+int apnerf_exclusive_scan_i64(long long n, const int64_t* in, int64_t* out, int64_t* total,
+                              int64_t* scratch, void* stream);
+long long apnerf_scan_scratch_elems(long long n);
+
+/* ---- kernel (4): packed scans, transmittance weights, accumulation ------------------- */
+
+/* nerfacc_cuda.inclusive_sum / exclusive_sum -- csrc/scan.cu:9-125 (backward = reverse scan). */
+int apnerf_packed_sum(int n_rays, const int64_t* chunk_starts, const int64_t* chunk_cnts,
+                      long long n_edges, const float* inputs, float* outputs, int inclusive,
+                      int normalize, int backward, void* stream);
+
+/* render_weight_from_density / render_transmittance_from_density -- nerfacc/volrend.py:212-267,
+ * 315-365, fused (sigma*dt, exclusive sum, exp, alpha, weight).  prefix_trans and any output
+ * may be NULL. */
+int apnerf_weights_from_density(int n_rays, const int64_t* chunk_starts, const int64_t* chunk_cnts,
+                                long long n_samples, const float* t_starts, const float* t_ends,
+                                const float* sigmas, const float* prefix_trans, float* weights,
+                                float* trans, float* alphas, void* stream);
+/* autograd of the above (reference: _ExclusiveSum.backward, nerfacc/scan.py:206-229, plus the
+ * ATen elementwise graph of volrend.py:259-267). */
+int apnerf_weights_from_density_bwd(int n_rays, const int64_t* chunk_starts, const int64_t* chunk_cnts,
+                                    long long n_samples, const float* t_starts, const float* t_ends,
+                                    const float* sigmas, const float* prefix_trans,
+                                    const float* g_weights, const float* g_trans, const float* g_alphas,
+                                    float* g_sigmas, float* g_prefix, void* stream);
+
+/* accumulate_along_rays / accumulate_along_rays_ -- nerfacc/volrend.py:486-576:
+ * outputs[ray_indices[i], :] += weights[i] * values[i, :] (values NULL: D == 1, += weights). */
+int apnerf_accumulate_along_rays(long long n_samples, int D, const float* weights, const float* values,
+                                 const int64_t* ray_indices, float* outputs, void* stream);
+int apnerf_accumulate_along_rays_bwd(long long n_samples, int D, const float* weights,
+                                     const float* values, const int64_t* ray_indices,
+                                     const float* g_outputs, float* g_weights, float* g_values,
+                                     void* stream);
+
+/* pack_info -- nerfacc/pack.py:10-49.  packed_info [n_rays, 2] int64 (start, count).
+ * scratch: 2 * n_rays + apnerf_scan_scratch_elems(n_rays) int64 elements. */
+int apnerf_pack_info(long long n_samples, const int64_t* ray_indices, int n_rays, int64_t* packed_info,
+                     int64_t* scratch, void* stream);
+
+/* ---- kernels (2) + (3): hash-grid encode and the fused field (hash grid + MLPs) -------- */
+
+/* Stand-alone multiresolution hash-grid encode (tcnn HashGrid part of
+ * tcnn.NetworkWithInputEncoding, perception/models/radiance_fields/ngp.py:123-133), used for the
+ * bit-exact cell-index parity check.  x01 [n,3] f32 in aabb-normalised coordinates;
+ * meta_host: HOST array [n_levels][5] u32 {scale (f32 bits), resolution, entries, first entry,
+ * hashed}; table fp16 [entries,4]; out_enc fp16 [n, n_levels*4] (NULL ok); out_idx u32
+ * [n, n_levels, 8] table-entry indices (NULL ok). */
+int apnerf_hashgrid_encode(long long n, const float* x01, int n_levels, const uint32_t* meta_host,
+                           const void* table, void* out_enc, uint32_t* out_idx, void* stream);
+
+/* NGPRadianceField.query_density / forward -- perception/models/radiance_fields/ngp.py:171-238
+ * (tcnn modules :107-169), one fused kernel.  Sample points are either positions(+directions)
+ * [n,3] or ray samples (ray_idx i32 [n], t_starts/t_ends [n], rays_o/rays_d [n_rays,3]) whose
+ * midpoints are formed in-kernel exactly as perception/models/utils.py:833-836.  n_dev
+ * (device int32, may be NULL) overrides n for device-driven loops; max_tiles then bounds the
+ * grid.  aabb_host: HOST float[6].  weights: fp16 blob of apnerf_field_weight_bytes() bytes in
+ * UMMA K-major layout (see csrc/field.cuh).  Outputs: density [n]; rgb(i,c) at
+ * rgb[c*rgb_ch + i*rgb_row]; sem(i,c) likewise for c < n_sem; feat fp16 [n,15] (NULL ok). */
+int apnerf_field_forward(long long n, const int* n_dev, const float* positions, const float* directions,
+                         const int* ray_idx, const float* t_starts, const float* t_ends,
+                         const float* rays_o, const float* rays_d, const float* aabb_host,
+                         int n_levels, const uint32_t* meta_host, const void* table,
+                         const void* weights, float* density, float* rgb, long long rgb_row,
+                         long long rgb_ch, float* sem, long long sem_row, long long sem_ch, int n_sem,
+                         void* feat, int density_only, long long max_tiles, void* stream);
+int apnerf_field_weight_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APNERF_H */

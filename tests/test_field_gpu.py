@@ -1,0 +1,88 @@
+"""GPU: radiance field (hash-grid encode + fused tcgen05 MLPs) against the CPU oracle.
+Hash-grid cell indices and the fp16 encoding are integer / deterministic work: bit-exact.
+MLP outputs: fp16 operands with fp32 accumulation -> <= 1e-3 absolute on colour (north_star);
+the tolerances are written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+AABB = [-6.4, -0.2, -6.4, 6.4, 12.6, 6.4]
+
+
+def _field(apnerf, C=29, seed=2):
+    from apnerf import synthetic
+
+    f = apnerf.NGPRadianceField(AABB, layers=2, num_semantic_classes=C)
+    synthetic.init_trained_like(f, seed=seed)
+    return f.to(DEV).eval()
+
+
+def _oracle_params(oracle, f, C=29):
+    sem = f.mlp_sem.params.detach().cpu().numpy() if C > 0 else None
+    return oracle.FieldParams(f.mlp_base.params.detach().cpu().numpy(), f.mlp_head.params.detach().cpu().numpy(), sem,
+                              num_semantic_classes=C)
+
+
+def test_hashgrid_indices_and_encoding_bit_exact(apnerf, oracle):
+    import ctypes
+    from apnerf._lib import call
+    from apnerf.radiance_fields.ngp import hashgrid_levels
+
+    meta, total = hashgrid_levels(16, 16, 4096, 19)
+    g = torch.Generator().manual_seed(5)
+    table = (torch.rand((total, 4), generator=g) * 2 - 1).to(torch.float16)
+    n = 20000
+    x = torch.rand((n, 3), generator=g)
+    x[:64] = x[:64] * 1.5 - 0.25  # some points outside the unit cube (selector-masked in the field)
+    x[64] = torch.tensor([0.0, 0.5, 1.0])
+    enc = torch.empty((n, 64), dtype=torch.float16, device=DEV)
+    idx = torch.empty((n, 16, 8), dtype=torch.int32, device=DEV)
+    call("apnerf_hashgrid_encode", n, x.to(DEV), 16, meta.ctypes.data_as(ctypes.c_void_p), table.to(DEV), enc, idx)
+    oenc, oidx = oracle.hashgrid_encode(x.numpy(), table.numpy(), oracle.hashgrid_meta()[0], want_indices=True)
+    assert (idx.cpu().numpy().view(np.uint32) == oidx).all(), "hash-grid cell indices must be bit-exact"
+    assert (enc.cpu().numpy().view(np.uint16) == oenc.view(np.uint16)).all(), "fp16 encoding must be bit-exact"
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 5000, 40000])
+def test_field_forward_matches_oracle(apnerf, oracle, n):
+    f = _field(apnerf)
+    fp = _oracle_params(oracle, f)
+    g = torch.Generator().manual_seed(n)
+    lo, hi = torch.tensor(AABB[:3]), torch.tensor(AABB[3:])
+    pos = lo + (hi - lo) * (torch.rand((n, 3), generator=g) * 1.1 - 0.05)  # a few outside the aabb
+    dirs = torch.randn((n, 3), generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        rgb, density, sem = f(pos.to(DEV), dirs.to(DEV))
+        d2, feat = f.query_density(pos.to(DEV), return_feat=True)
+    orgb, odens, osem = oracle.field_forward(pos.numpy(), dirs.numpy(), np.asarray(AABB, np.float32), fp)
+    rgb, density, sem, d2 = (t.cpu().numpy() for t in (rgb, density, sem, d2))
+    assert rgb.shape == (n, 3) and density.shape == (n, 1) and sem.shape == (n, 29)
+    assert np.isfinite(rgb).all() and np.isfinite(sem).all()
+    assert (density == d2).all(), "query_density and forward disagree"
+    outside = ((pos < lo) | (pos > hi)).any(-1).numpy()
+    assert (density[outside] == 0).all()
+    # density = exp(fp16 logit - 1): one fp16 ulp of the logit (2^-10 relative at |x|~1..2, more for
+    # larger logits) is the expected deviation; allow 2 % relative
+    rel = np.abs(density - odens) / np.maximum(np.abs(odens), 1e-6)
+    assert np.quantile(rel, 0.999) <= 2e-2 and np.median(rel) <= 1e-3, (np.quantile(rel, 0.999), np.median(rel))
+    assert np.abs(rgb - orgb).max() <= 1e-3 * 4, np.abs(rgb - orgb).max()       # worst case
+    assert np.quantile(np.abs(rgb - orgb), 0.999) <= 1e-3                       # north_star tolerance
+    assert np.quantile(np.abs(sem - osem), 0.999) <= 4e-3 * max(1.0, np.abs(osem).max())
+
+
+def test_field_without_semantics(apnerf, oracle):
+    f = _field(apnerf, C=0)
+    fp = _oracle_params(oracle, f, C=0)
+    g = torch.Generator().manual_seed(1)
+    lo, hi = torch.tensor(AABB[:3]), torch.tensor(AABB[3:])
+    pos = lo + (hi - lo) * torch.rand((1000, 3), generator=g)
+    dirs = torch.randn((1000, 3), generator=g)
+    dirs = dirs / dirs.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        out = f(pos.to(DEV), dirs.to(DEV))
+    assert len(out) == 2
+    orgb, odens = oracle.field_forward(pos.numpy(), dirs.numpy(), np.asarray(AABB, np.float32), fp)
+    assert np.quantile(np.abs(out[0].cpu().numpy() - orgb), 0.999) <= 1e-3
