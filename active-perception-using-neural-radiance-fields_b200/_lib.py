@@ -100,13 +100,22 @@ class _Lib:
                 conv.append(a)
         if len(conv) == len(fn.argtypes) - 1:
             conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
         rc = fn(*conv)
         if rc != 0:
             raise RuntimeError(f"{name} failed (code {rc}): {self.last_error()}")
 
 
+# how many times each C-ABI entry point was invoked (bench.py turns this into kernel launches)
+LAUNCHES = {}
+KERNELS_PER_CALL = {"apnerf_exclusive_scan_i64": 3, "apnerf_pack_info": 5}
+
 LIB = _Lib()
 call = LIB.call
+
+
+def kernel_launches() -> int:
+    return sum(n * KERNELS_PER_CALL.get(name, 1) for name, n in LAUNCHES.items())
 
 
 def require_cuda(*tensors):

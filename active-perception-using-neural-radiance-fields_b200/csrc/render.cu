@@ -1,0 +1,486 @@
+// The device-driven test-mode renderer and the predictive-information scorer (kernels 1, 4, 5 in
+// their fused form).  Replaces, on the reference side,
+//   Dataset.generate_image_rays                     perception/data_proc/habitat_to_data.py:274-301
+//   render_probablistic_image_with_occgrid_test     perception/models/utils.py:782-1032
+//   render_image_with_occgrid_test                  perception/models/utils.py:555-779
+//   ActiveNeRFMapper.probablistic_uncertainty       scripts/pipeline.py:727-781 (the arithmetic)
+//
+// A "call" is one view rendered through one ensemble member (R rays).  The reference marches a
+// call in iterations of n = max(min(R // n_alive, 64), min_samples) samples per live ray, with
+// three host synchronisations per iteration.  Here a whole batch of calls advances in lock step
+// with the SAME per-call schedule, but every decision (n_alive, n, termination, compaction of
+// the live-ray list, sample counts) is taken on the device: the host only enqueues a fixed
+// kernel sequence per iteration and never reads anything back until the scores are done.
+//
+// Per-ray running state lives in HBM as structure-of-arrays [channel][ray]:
+//   0-2 rgb | 3 opacity | 4 depth | 5-7 rgb_var | 8 depth_var | 9.. semantic logits (C)
+#include "march.cuh"
+
+namespace apnerf {
+
+constexpr int ST_RGB = 0, ST_OPA = 3, ST_DEPTH = 4, ST_RGBVAR = 5, ST_DVAR = 8, ST_SEM = 9;
+constexpr int MAX_ITER_SAMPLES = 64;  // the reference caps n at 64 (utils.py:902)
+
+// counters[0] live rays this iteration, [1] live rays being collected for the next one,
+// [2] samples emitted this iteration, [3] total iterations executed with work
+__global__ void render_schedule_kernel(int n_calls, int rays_per_call, int max_samples, int min_samples,
+                                       int* __restrict__ n_alive_acc, int* __restrict__ n_samp,
+                                       int* __restrict__ iter_samples, int* __restrict__ counters) {
+  for (int c = threadIdx.x; c < n_calls; c += blockDim.x) {
+    const int na = n_alive_acc[c];
+    n_alive_acc[c] = 0;
+    int n = 0;
+    if (iter_samples[c] < max_samples && na > 0) {  // utils.py:896-903
+      n = max(min(rays_per_call / na, MAX_ITER_SAMPLES), min_samples);
+      iter_samples[c] += n;
+    }
+    n_samp[c] = n;
+  }
+  if (threadIdx.x == 0) {
+    counters[0] = counters[1];
+    counters[1] = 0;
+    counters[2] = 0;
+    if (counters[0] > 0) counters[3] += 1;
+  }
+}
+
+// rays from camera poses (OpenGL convention), optionally subsampled by an index list.
+__global__ void __launch_bounds__(256) generate_rays_kernel(int n_views, const float* __restrict__ c2w,  // [V,3,4]
+                                                            int width, int height, float focal, int n_keep,
+                                                            const int* __restrict__ keep_idx,
+                                                            float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const long long total = (long long)n_views * n_keep;
+  const float cx = (float)(width * 0.5), cy = (float)(height * 0.5);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)blockDim.x * gridDim.x) {
+    const int v = (int)(t / n_keep), k = (int)(t % n_keep);
+    const int pix = keep_idx ? keep_idx[k] : k;
+    const float x = (float)(pix % width), y = (float)(pix / width);
+    const float* m = c2w + 12 * v;
+    // habitat_to_data.py:285-295: [(x - cx + 0.5) / fx, (y - cy + 0.5) / fy * -1, -1]
+    const float c0 = __fdiv_rn(__fadd_rn(__fsub_rn(x, cx), 0.5f), focal);
+    const float c1 = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(y, cy), 0.5f), focal), -1.0f);
+    const float c2 = -1.0f;
+    float d[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      d[i] = __fadd_rn(__fadd_rn(__fmul_rn(c0, m[4 * i + 0]), __fmul_rn(c1, m[4 * i + 1])), __fmul_rn(c2, m[4 * i + 2]));
+    const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      rays_o[3 * t + i] = m[4 * i + 3];
+      rays_d[3 * t + i] = __fdiv_rn(d[i], nrm);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) render_init_kernel(int n_rays, int rays_per_call, const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, GridView g,
+                                                          float near_plane, int n_state, float* __restrict__ state,
+                                                          float* __restrict__ t_min, float* __restrict__ t_max,
+                                                          uint8_t* __restrict__ hit, float* __restrict__ near,
+                                                          int* __restrict__ alive, int* __restrict__ n_alive_acc,
+                                                          int* __restrict__ iter_samples, int* __restrict__ total_samples,
+                                                          int n_calls, int* __restrict__ counters) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += blockDim.x * gridDim.x) {
+    const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+    const float inv[3] = {__frcp_rn(rays_d[3 * r]), __frcp_rn(rays_d[3 * r + 1]), __frcp_rn(rays_d[3 * r + 2])};
+    float t0, t1;
+    // ray_aabb_intersect with the default +-inf planes, miss value +inf (utils.py:882, grid.py:14-21)
+    const bool h = ray_aabb(o, inv, -INFINITY, INFINITY, g.aabbs, t0, t1);
+    t_min[r] = h ? t0 : INFINITY;
+    t_max[r] = h ? t1 : INFINITY;
+    hit[r] = h ? 1 : 0;
+    near[r] = near_plane;
+    alive[r] = r;
+    for (int c = 0; c < n_state; ++c) state[(size_t)c * n_rays + r] = 0.f;
+  }
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < n_calls; c += blockDim.x) {
+      n_alive_acc[c] = rays_per_call;
+      iter_samples[c] = 0;
+      total_samples[c] = 0;
+    }
+    if (threadIdx.x == 0) counters[0] = 0, counters[1] = n_rays, counters[2] = 0, counters[3] = 0;
+  }
+}
+
+struct LocalSink {
+  float* ts;
+  float* te;
+  __device__ __forceinline__ void operator()(float t_last, float t_next, bool, int i_sample, int) {
+    ts[i_sample] = t_last;
+    te[i_sample] = t_next;
+  }
+};
+
+// One thread per live ray: march up to n samples from the ray's previous terminate plane and
+// append them to the compact per-iteration sample list (warp-aggregated reservation keeps the
+// samples of neighbouring rays adjacent, which is what gives the hash-grid gather its locality).
+__global__ void __launch_bounds__(256) render_march_kernel(const int* counters_in, int rays_per_call,
+                                                           const int* __restrict__ alive, const int* __restrict__ n_samp,
+                                                           const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                           GridView g, const float* __restrict__ t_min,
+                                                           const float* __restrict__ t_max, const uint8_t* __restrict__ hit,
+                                                           float* __restrict__ near, float far_plane, float step_size,
+                                                           float cone_angle, int* __restrict__ entry_base,
+                                                           int* __restrict__ entry_cnt, int* __restrict__ s_ray,
+                                                           float* __restrict__ s_ts, float* __restrict__ s_te,
+                                                           int* counters) {
+  const int n_live = counters_in[0];
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n_live + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += blockDim.x * gridDim.x) {
+    float ts[MAX_ITER_SAMPLES], te[MAX_ITER_SAMPLES];
+    int k = 0, ray = -1;
+    if (i < n_live) {
+      ray = alive[i];
+      const int n = n_samp[ray / rays_per_call];
+      if (n > 0) {
+        const float o[3] = {rays_o[3 * ray], rays_o[3 * ray + 1], rays_o[3 * ray + 2]};
+        const float d[3] = {rays_d[3 * ray], rays_d[3 * ray + 1], rays_d[3 * ray + 2]};
+        const float tsorted[2] = {t_min[ray], t_max[ray]};
+        const uint8_t h = hit[ray];
+        LocalSink sink{ts, te};
+        int n_iv;
+        float t_term;
+        k = march_ray(g, o, d, near[ray], far_plane, &h, tsorted, nullptr, step_size, cone_angle, n, sink, n_iv, t_term);
+        near[ray] = t_term;  // utils.py:1002
+      }
+    }
+    // warp-aggregated reservation of k slots
+    int inc = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
+    int warp_base = 0;
+    if (lane == 31 && warp_total > 0) warp_base = atomicAdd(counters + 2, warp_total);
+    warp_base = __shfl_sync(0xffffffffu, warp_base, 31);
+    const int base = warp_base + inc - k;
+    if (i < n_live) {
+      entry_base[i] = base;
+      entry_cnt[i] = k;
+      for (int j = 0; j < k; ++j) {
+        s_ray[base + j] = ray;
+        s_ts[base + j] = ts[j];
+        s_te[base + j] = te[j];
+      }
+    }
+  }
+}
+
+// One thread per live ray: transmittance weights of this iteration's samples (prefix = 1 - the
+// accumulated opacity, utils.py:937-944), alpha_thre filter, accumulation of rgb / opacity /
+// depth / semantic logits, then the variance terms against the UPDATED running rgb / depth
+// (utils.py:957-999), next ray mask (utils.py:1004-1009) and compaction of the live list.
+template <bool PROB>
+__global__ void __launch_bounds__(128) render_composite_kernel(
+    const int* counters_in, int n_rays, int rays_per_call, int n_sem, long long s_cap,
+    const int* __restrict__ alive, const int* __restrict__ entry_base, const int* __restrict__ entry_cnt,
+    const float* __restrict__ s_ts, const float* __restrict__ s_te, const float* __restrict__ dens,
+    const float* __restrict__ rgb_s, const float* __restrict__ sem_s, float* __restrict__ state, float alpha_thre,
+    float opc_thre, const int* __restrict__ n_samp, const int* __restrict__ iter_samples, int max_samples,
+    int* __restrict__ alive_next, int* __restrict__ n_alive_acc, int* __restrict__ total_samples,
+    int* counters) {
+  const int n_live = counters_in[0];
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n_live + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += blockDim.x * gridDim.x) {
+    bool keep = false;
+    int ray = -1, call = -1, n_vis = 0;
+    if (i < n_live) {
+      ray = alive[i];
+      call = ray / rays_per_call;
+      const int base = entry_base[i], k = entry_cnt[i];
+      float* st = state + ray;
+      const size_t NR = (size_t)n_rays;
+      float opac = st[ST_OPA * NR];
+      if (k > 0) {
+        const float prefix = __fsub_rn(1.0f, opac);
+        float rgb[3] = {st[0], st[NR], st[2 * NR]};
+        float depth = st[ST_DEPTH * NR];
+        float sem[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sem[c] = (c < n_sem) ? st[(ST_SEM + c) * NR] : 0.f;
+        float esum = 0.f;
+        for (int j = 0; j < k; ++j) {
+          const int s = base + j;
+          const float t0 = s_ts[s], t1 = s_te[s];
+          const float sdt = __fmul_rn(dens[s], __fsub_rn(t1, t0));
+          const float alpha = __fsub_rn(1.0f, expf(-sdt));
+          const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
+          esum = __fadd_rn(esum, sdt);
+          if (alpha_thre > 0.f && !(alpha >= alpha_thre)) continue;
+          ++n_vis;
+          const float tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rgb[c] = __fadd_rn(rgb[c], __fmul_rn(w, rgb_s[c * s_cap + s]));
+          opac = __fadd_rn(opac, w);
+          depth = __fadd_rn(depth, __fmul_rn(w, tmid));
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < n_sem) sem[c] = __fadd_rn(sem[c], __fmul_rn(w, sem_s[c * s_cap + s]));
+        }
+        if (PROB) {
+          float rv[3] = {st[ST_RGBVAR * NR], st[(ST_RGBVAR + 1) * NR], st[(ST_RGBVAR + 2) * NR]};
+          float dv = st[ST_DVAR * NR];
+          esum = 0.f;
+          for (int j = 0; j < k; ++j) {
+            const int s = base + j;
+            const float t0 = s_ts[s], t1 = s_te[s];
+            const float sdt = __fmul_rn(dens[s], __fsub_rn(t1, t0));
+            const float alpha = __fsub_rn(1.0f, expf(-sdt));
+            const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
+            esum = __fadd_rn(esum, sdt);
+            if (alpha_thre > 0.f && !(alpha >= alpha_thre)) continue;
+            const float tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const float df = __fsub_rn(rgb_s[c * s_cap + s], rgb[c]);
+              rv[c] = __fadd_rn(rv[c], __fmul_rn(w, __fmul_rn(df, df)));
+            }
+            const float dd = __fsub_rn(tmid, depth);
+            dv = __fadd_rn(dv, __fmul_rn(w, __fmul_rn(dd, dd)));
+          }
+#pragma unroll
+          for (int c = 0; c < 3; ++c) st[(ST_RGBVAR + c) * NR] = rv[c];
+          st[ST_DVAR * NR] = dv;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) st[c * NR] = rgb[c];
+        st[ST_OPA * NR] = opac;
+        st[ST_DEPTH * NR] = depth;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < n_sem) st[(ST_SEM + c) * NR] = sem[c];
+      }
+      const int n = n_samp[call];
+      keep = (n > 0) && (opac <= opc_thre) && (k == n) && (iter_samples[call] < max_samples);
+    }
+    // compaction of the live list (order-preserving inside a warp) + per-call live counts
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    int warp_base = 0;
+    if (lane == 0 && ballot) warp_base = atomicAdd(counters + 1, __popc(ballot));
+    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+    if (keep) alive_next[warp_base + __popc(ballot & ((1u << lane) - 1u))] = ray;
+    const unsigned peers = __match_any_sync(0xffffffffu, call);
+    const int vis_sum = __reduce_add_sync(peers, n_vis);
+    if (call >= 0 && lane == __ffs(peers) - 1) {
+      const int kept = __popc(ballot & peers);
+      if (kept) atomicAdd(n_alive_acc + call, kept);
+      if (vis_sum) atomicAdd(total_samples + call, vis_sum);
+    }
+  }
+}
+
+// rgb += bkgd * (1 - opacity); depth /= max(opacity, eps)  (utils.py:1012-1013) and
+// structure-of-arrays -> the reference's [n_rays, D] outputs.
+__global__ void __launch_bounds__(256) render_finalize_kernel(int n_rays, int n_sem, const float* __restrict__ state,
+                                                              float b0, float b1, float b2, float* __restrict__ rgb,
+                                                              float* __restrict__ rgb_var, float* __restrict__ opacity,
+                                                              float* __restrict__ depth, float* __restrict__ depth_var,
+                                                              float* __restrict__ sem) {
+  const size_t NR = (size_t)n_rays;
+  const float bk[3] = {b0, b1, b2};
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += blockDim.x * gridDim.x) {
+    const float op = state[ST_OPA * NR + r];
+    if (rgb)
+      for (int c = 0; c < 3; ++c) rgb[3 * r + c] = __fadd_rn(state[c * NR + r], __fmul_rn(bk[c], __fsub_rn(1.0f, op)));
+    if (rgb_var)
+      for (int c = 0; c < 3; ++c) rgb_var[3 * r + c] = state[(ST_RGBVAR + c) * NR + r];
+    if (opacity) opacity[r] = op;
+    if (depth) depth[r] = __fdiv_rn(state[ST_DEPTH * NR + r], fmaxf(op, 1.1920928955078125e-07f));
+    if (depth_var) depth_var[r] = state[ST_DVAR * NR + r];
+    if (sem)
+      for (int c = 0; c < n_sem; ++c) sem[(size_t)r * n_sem + c] = state[(ST_SEM + c) * NR + r];
+  }
+}
+
+// Predictive information of an ensemble's renders (scripts/pipeline.py:727-781), per pixel in
+// float64 like the reference's numpy, reduced to four sums per trajectory:
+//   [0] sum over pixels x 3 channels of  H(ensemble rgb var) - mean_m H(rgb var_m)
+//   [1] sum over pixels of the same for depth
+//   [2] sum over pixels of  H(mean_m softmax) - mean_m H(softmax_m)
+//   [3] sum over pixels of  Hb(mean_m acc) - mean_m Hb(acc_m)
+// The host divides by the element counts and applies the x3 / x2 weights (pipeline.py:772-790).
+struct EnsembleStates {
+  const float* s[4];
+};
+
+__device__ __forceinline__ double gauss_entropy(double var) { return log(2.0 * M_PI * M_E * var + 1e-4) / 2.0; }
+__device__ __forceinline__ double bern_entropy(double a) {
+  return -(a + 1e-4) * log(a + 1e-4) - (1.0 - a + 1e-4) * log(1.0 - a + 1e-4);
+}
+
+__global__ void __launch_bounds__(128) score_views_kernel(int n_members, EnsembleStates es, int n_rays,
+                                                          int rays_per_view, int n_sem,
+                                                          const int* __restrict__ view_traj, int n_traj,
+                                                          double* __restrict__ sums) {
+  extern __shared__ double acc_s[];  // [n_traj][4]
+  for (int i = threadIdx.x; i < n_traj * 4; i += blockDim.x) acc_s[i] = 0.0;
+  __syncthreads();
+  const size_t NR = (size_t)n_rays;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += blockDim.x * gridDim.x) {
+    const int traj = view_traj[r / rays_per_view];
+    if (traj < 0) continue;
+    double t_rgb = 0.0, t_depth, t_sem = 0.0, t_occ;
+    for (int c = 0; c < 3; ++c) {
+      double vs = 0.0, hs = 0.0;
+      for (int m = 0; m < n_members; ++m) {
+        const double v = (double)es.s[m][(ST_RGBVAR + c) * NR + r];
+        vs += v;
+        hs += gauss_entropy(v);
+      }
+      t_rgb += gauss_entropy(vs / 2.0) - hs / n_members;  // pipeline.py:733 hard-codes "/ 2"
+    }
+    {
+      double vs = 0.0, hs = 0.0;
+      for (int m = 0; m < n_members; ++m) {
+        const double v = (double)es.s[m][ST_DVAR * NR + r];
+        vs += v;
+        hs += gauss_entropy(v);
+      }
+      t_depth = gauss_entropy(vs / 2.0) - hs / n_members;
+    }
+    if (n_sem > 0) {
+      double pm[32];
+      for (int c = 0; c < 32; ++c) pm[c] = 0.0;
+      double hs = 0.0;
+      for (int m = 0; m < n_members; ++m) {
+        const float* sp = es.s[m] + ST_SEM * NR + r;
+        double mx = -1e300;
+        for (int c = 0; c < n_sem; ++c) mx = fmax(mx, (double)sp[c * NR]);
+        double den = 0.0;
+        for (int c = 0; c < n_sem; ++c) den += exp((double)sp[c * NR] - mx);
+        double h = 0.0;
+        for (int c = 0; c < n_sem; ++c) {
+          const double p = exp((double)sp[c * NR] - mx) / den;
+          pm[c] += p;
+          h -= (p + 1e-4) * log(p + 1e-4);
+        }
+        hs += h;
+      }
+      double he = 0.0;
+      for (int c = 0; c < n_sem; ++c) {
+        const double p = pm[c] / n_members;
+        he -= (p + 1e-4) * log(p + 1e-4);
+      }
+      t_sem = he - hs / n_members;
+    }
+    {
+      double as = 0.0, hs = 0.0;
+      for (int m = 0; m < n_members; ++m) {
+        const double a = (double)es.s[m][ST_OPA * NR + r];
+        as += a;
+        hs += bern_entropy(a);
+      }
+      t_occ = bern_entropy(as / n_members) - hs / n_members;
+    }
+    atomicAdd(&acc_s[traj * 4 + 0], t_rgb);
+    atomicAdd(&acc_s[traj * 4 + 1], t_depth);
+    atomicAdd(&acc_s[traj * 4 + 2], t_sem);
+    atomicAdd(&acc_s[traj * 4 + 3], t_occ);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_traj * 4; i += blockDim.x)
+    if (acc_s[i] != 0.0) atomicAdd(sums + i, acc_s[i]);
+}
+
+}  // namespace apnerf
+
+using namespace apnerf;
+
+APNERF_API int apnerf_generate_rays(int n_views, const float* c2w, int width, int height, float focal, int n_keep,
+                                    const int* keep_idx, float* rays_o, float* rays_d, void* stream) {
+  const long long total = (long long)n_views * n_keep;
+  if (total == 0) return 0;
+  generate_rays_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(n_views, c2w, width, height, focal,
+                                                                                  n_keep, keep_idx, rays_o, rays_d);
+  APNERF_CHECK_LAUNCH("generate_rays_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_render_init(int n_rays, int rays_per_call, const float* rays_o, const float* rays_d, int rx,
+                                  int ry, int rz, const uint8_t* binaries, const float* aabbs, float near_plane,
+                                  int n_state, float* state, float* t_min, float* t_max, uint8_t* hit, float* near,
+                                  int* alive, int* n_alive_acc, int* iter_samples, int* total_samples, int n_calls,
+                                  int* counters, void* stream) {
+  if (n_rays == 0) return 0;
+  GridView g{binaries, aabbs, 1, rx, ry, rz};
+  render_init_kernel<<<grid_for(n_rays, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      n_rays, rays_per_call, rays_o, rays_d, g, near_plane, n_state, state, t_min, t_max, hit, near, alive,
+      n_alive_acc, iter_samples, total_samples, n_calls, counters);
+  APNERF_CHECK_LAUNCH("render_init_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_render_schedule(int n_calls, int rays_per_call, int max_samples, int min_samples,
+                                      int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, void* stream) {
+  render_schedule_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_calls, rays_per_call, max_samples, min_samples,
+                                                             n_alive_acc, n_samp, iter_samples, counters);
+  APNERF_CHECK_LAUNCH("render_schedule_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* alive, const int* n_samp,
+                                   const float* rays_o, const float* rays_d, int rx, int ry, int rz,
+                                   const uint8_t* binaries, const float* aabbs, const float* t_min, const float* t_max,
+                                   const uint8_t* hit, float* near, float far_plane, float step_size, float cone_angle,
+                                   int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
+                                   int* counters, void* stream) {
+  if (max_live == 0) return 0;
+  GridView g{binaries, aabbs, 1, rx, ry, rz};
+  render_march_kernel<<<grid_for(max_live, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+      counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
+      cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, counters);
+  APNERF_CHECK_LAUNCH("render_march_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem, long long s_cap,
+                                       const int* alive, const int* entry_base, const int* entry_cnt,
+                                       const float* s_ts, const float* s_te, const float* dens, const float* rgb_s,
+                                       const float* sem_s, float* state, float alpha_thre, float opc_thre,
+                                       const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
+                                       int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
+                                       void* stream) {
+  if (max_live == 0) return 0;
+  APNERF_REQUIRE(n_sem >= 0 && n_sem <= 32, "render_composite: at most 32 semantic classes");
+  const int grid = grid_for(max_live, 128, 16);
+  if (probabilistic)
+    render_composite_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        counters, n_rays, rays_per_call, n_sem, s_cap, alive, entry_base, entry_cnt, s_ts, s_te, dens, rgb_s, sem_s,
+        state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters);
+  else
+    render_composite_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        counters, n_rays, rays_per_call, n_sem, s_cap, alive, entry_base, entry_cnt, s_ts, s_te, dens, rgb_s, sem_s,
+        state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters);
+  APNERF_CHECK_LAUNCH("render_composite_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_render_finalize(int n_rays, int n_sem, const float* state, float bkgd_r, float bkgd_g,
+                                      float bkgd_b, float* rgb, float* rgb_var, float* opacity, float* depth,
+                                      float* depth_var, float* sem, void* stream) {
+  if (n_rays == 0) return 0;
+  render_finalize_kernel<<<grid_for(n_rays, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      n_rays, n_sem, state, bkgd_r, bkgd_g, bkgd_b, rgb, rgb_var, opacity, depth, depth_var, sem);
+  APNERF_CHECK_LAUNCH("render_finalize_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_score_views(int n_members, const float* state0, const float* state1, const float* state2,
+                                  const float* state3, int n_rays, int rays_per_view, int n_sem,
+                                  const int* view_traj, int n_traj, double* sums, void* stream) {
+  if (n_rays == 0) return 0;
+  APNERF_REQUIRE(n_members >= 1 && n_members <= 4, "score_views: 1..4 ensemble members");
+  APNERF_REQUIRE(n_traj >= 1 && n_traj <= 1024, "score_views: 1..1024 trajectories");
+  EnsembleStates es{{state0, state1, state2, state3}};
+  score_views_kernel<<<grid_for(n_rays, 128, 8), 128, n_traj * 4 * sizeof(double), (cudaStream_t)stream>>>(
+      n_members, es, n_rays, rays_per_view, n_sem, view_traj, n_traj, sums);
+  APNERF_CHECK_LAUNCH("score_views_kernel");
+  return 0;
+}

@@ -1,0 +1,190 @@
+"""Candidate-trajectory scoring: render the planner's candidate views through every ensemble
+member and reduce them to predictive information -- the caller side of the hot path.
+
+Mirrors, on the reference side,
+  ActiveNeRFMapper.probablistic_uncertainty          scripts/pipeline.py:666-798
+  Dataset.render_probablistic_image_from_pose        perception/data_proc/habitat_to_data.py:413-549
+with the renders kept on the device (the reference copies six arrays per view to host numpy and
+reduces them in float64 numpy) and the planner's loop over trajectories (pipeline.py:1079-1085)
+folded into one batch.  Multi-GPU: views are sharded over ranks, each rank reduces its views to
+per-trajectory partial sums, and ONE all-reduce of [n_traj, 4] float64 finishes the job.
+"""
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import call
+from .render import FusedRenderer
+
+
+def quat_xyzw_to_matrix(q) -> np.ndarray:
+    """Rotation matrix of a (x, y, z, w) quaternion, as scipy's Rotation.from_quat(q).as_matrix()
+    (habitat_to_data.py:445-449)."""
+    x, y, z, w = (float(v) for v in q)
+    n = np.sqrt(x * x + y * y + z * z + w * w)
+    x, y, z, w = x / n, y / n, z / n, w / n
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)],
+    ], dtype=np.float64)
+
+
+def poses_to_c2w(poses: np.ndarray) -> np.ndarray:
+    """[n, 7] (x, y, z, qx, qy, qz, qw) float64 -> [n, 3, 4] float32 camera-to-world."""
+    poses = np.asarray(poses, dtype=np.float64).reshape(-1, 7)
+    out = np.empty((poses.shape[0], 3, 4), dtype=np.float32)
+    for i, p in enumerate(poses):
+        out[i, :, :3] = quat_xyzw_to_matrix(p[3:])
+        out[i, :, 3] = p[:3]
+    return out
+
+
+def uncertainty_view_indices(traj_len: int) -> np.ndarray:
+    """The 40 views the reference scores per trajectory (pipeline.py:687-689)."""
+    a = np.linspace(0, traj_len - 20, 20)
+    b = np.linspace(traj_len - 20, traj_len - 1, 20)
+    return np.hstack((a, b)).astype(int)
+
+
+class PredictiveInformationScorer:
+    """Renders views x ensemble members with the fused renderer and scores them on the device."""
+
+    def __init__(self, radiance_fields: Sequence[torch.nn.Module], estimators: Sequence[torch.nn.Module], width: int,
+                 height: int, focal: float, *, near_plane: float = 0.1, render_step_size: float = 1e-3,
+                 cone_angle: float = 0.004, alpha_thre: float = 0.01, scale: float = 1.0, max_samples: int = 1024,
+                 device="cuda:0", views_per_batch: int = 32):
+        assert 1 <= len(radiance_fields) <= 4 and len(radiance_fields) == len(estimators)
+        self.fields, self.estimators = list(radiance_fields), list(estimators)
+        self.width, self.height, self.focal = int(width), int(height), float(focal)
+        self.opts = dict(near_plane=near_plane, render_step_size=render_step_size, cone_angle=cone_angle,
+                         alpha_thre=alpha_thre, max_samples=max_samples)
+        self.device = torch.device(device)
+        self.n_sem = self.fields[0].num_semantic_classes
+        self.views_per_batch = int(views_per_batch)
+        # rounded-linspace subsample of the full image (habitat_to_data.py:462-467)
+        h, w = int(height * scale), int(width * scale)
+        self.rays_per_view = h * w
+        if self.rays_per_view == width * height:
+            self.keep_idx = None
+        else:
+            idx = np.round(np.linspace(0, width * height - 1, self.rays_per_view)).astype(np.int32)
+            self.keep_idx = torch.from_numpy(idx).to(self.device)
+        self.renderer = FusedRenderer(self.device, self.n_sem)
+        self._states = None
+        self._rays = None
+
+    def _buffers(self, n_views):
+        n_rays = n_views * self.rays_per_view
+        if self._rays is None or self._rays[0].shape[0] < n_rays:
+            self._rays = (torch.empty((n_rays, 3), device=self.device), torch.empty((n_rays, 3), device=self.device))
+            self._states = [torch.empty((9 + self.n_sem, n_rays), device=self.device) for _ in self.fields]
+        return n_rays
+
+    @torch.no_grad()
+    def partial_sums(self, c2w: torch.Tensor, view_traj: torch.Tensor, n_traj: int,
+                     sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """c2w [n_views, 3, 4] f32 and view_traj [n_views] i32 ON THE DEVICE -> float64 [n_traj, 4]
+        sums of the per-pixel (rgb, depth, sem, occ) predictive-information terms.  Everything is
+        enqueued on the current stream; nothing is read back."""
+        n_views = c2w.shape[0]
+        if sums is None:
+            sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
+        vb = self.views_per_batch
+        self._buffers(min(vb, n_views))
+        with torch.cuda.device(self.device):
+            for v0 in range(0, n_views, vb):
+                v1 = min(n_views, v0 + vb)
+                nr = (v1 - v0) * self.rays_per_view
+                rays_o, rays_d = self._rays[0][:nr], self._rays[1][:nr]
+                call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
+                     self.rays_per_view, self.keep_idx, rays_o, rays_d)
+                states = []
+                for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
+                    st = self._states[m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
+                    self.renderer.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
+                                         **self.opts)
+                    states.append(st)
+                states += [None] * (4 - len(states))
+                call("apnerf_score_views", len(self.fields), states[0], states[1], states[2], states[3], nr,
+                     self.rays_per_view, self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
+        return sums
+
+    @staticmethod
+    def finish(sums: np.ndarray, pixels_per_traj: np.ndarray) -> np.ndarray:
+        """[n_traj, 4] sums + pixel counts -> the four entries the reference logs per trajectory
+        (rgb, depth, 3 * sem, 2 * occ; pipeline.py:772-790).  Their row sum is the score."""
+        sums = np.asarray(sums, dtype=np.float64)
+        n = np.maximum(np.asarray(pixels_per_traj, dtype=np.float64), 1.0)[:, None]
+        terms = sums / n
+        terms[:, 0] /= 3.0  # the rgb mean runs over pixels x 3 channels
+        terms[:, 2] *= 3.0
+        terms[:, 3] *= 2.0
+        return terms
+
+    @torch.no_grad()
+    def score_trajectories(self, trajectories: List[np.ndarray], process_group=None) -> np.ndarray:
+        """Host-facing call: list of planner trajectories ([len, 7] pose arrays) -> [n_traj, 4]
+        predictive-information terms.  With torch.distributed initialised (or a process group
+        given) the views are sharded contiguously over the ranks."""
+        import torch.distributed as dist
+
+        poses, owner = [], []
+        for t, traj in enumerate(trajectories):
+            traj = np.asarray(traj)
+            idx = uncertainty_view_indices(len(traj)) if len(traj) >= 40 else np.arange(len(traj))
+            poses.append(traj[idx])
+            owner += [t] * len(idx)
+        poses = np.concatenate(poses, 0)
+        owner = np.asarray(owner, dtype=np.int32)
+        return self.score_views(poses, owner, len(trajectories), process_group=process_group)
+
+    @torch.no_grad()
+    def score_views(self, poses: np.ndarray, view_traj: np.ndarray, n_traj: int, process_group=None) -> np.ndarray:
+        import torch.distributed as dist
+
+        use_dist = dist.is_available() and dist.is_initialized()
+        rank = dist.get_rank(process_group) if use_dist else 0
+        world = dist.get_world_size(process_group) if use_dist else 1
+        n_views = poses.shape[0]
+        lo, hi = shard_range(n_views, rank, world)
+        c2w_host = torch.from_numpy(poses_to_c2w(poses[lo:hi])).pin_memory()
+        vt_host = torch.from_numpy(np.ascontiguousarray(view_traj[lo:hi], dtype=np.int32)).pin_memory()
+        c2w = c2w_host.to(self.device, non_blocking=True)
+        vt = vt_host.to(self.device, non_blocking=True)
+        sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
+        if hi > lo:
+            self.partial_sums(c2w, vt, n_traj, sums)
+        if use_dist and world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=process_group)
+        counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
+        return self.finish(sums.cpu().numpy(), counts)
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced [lo, hi) slice of n units for `rank` of `world`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def probablistic_uncertainty(radiance_fields, estimators, trajectory, *, img_w, img_h, focal, near_plane,
+                             render_step_size, cone_angle, alpha_thre, scale=0.1, device="cuda:0", log=None) -> float:
+    """Drop-in for the body of ActiveNeRFMapper.probablistic_uncertainty (pipeline.py:666-798):
+    returns the trajectory's predictive information; appends the four logged terms to `log`."""
+    key = (id(radiance_fields[0]), img_w, img_h, float(focal), float(scale), str(device))
+    scorer = _SCORERS.get(key)
+    if scorer is None:
+        scorer = PredictiveInformationScorer(radiance_fields, estimators, img_w, img_h, focal, near_plane=near_plane,
+                                             render_step_size=render_step_size, cone_angle=cone_angle,
+                                             alpha_thre=alpha_thre, scale=scale, device=device, views_per_batch=40)
+        _SCORERS.clear()
+        _SCORERS[key] = scorer
+    terms = scorer.score_trajectories([np.asarray(trajectory)])[0]
+    if log is not None:
+        log.append(terms.tolist())
+    return float(terms.sum())
+
+
+_SCORERS = {}

@@ -124,6 +124,58 @@ int apnerf_field_forward(long long n, const int* n_dev, const float* positions, 
                          void* feat, int density_only, long long max_tiles, void* stream);
 int apnerf_field_weight_bytes(void);
 
+/* ---- the device-driven test-mode renderer + scorer (kernels 1, 4, 5 fused) -------------
+ * One "call" = one view through one ensemble member (rays_per_call rays); a batch of calls
+ * advances in lock step with the reference's per-call marching schedule
+ * (perception/models/utils.py:896-1009) decided entirely on the device.
+ * Per-ray state: float [n_state = 9 + n_sem][n_rays] structure-of-arrays
+ *   (0-2 rgb, 3 opacity, 4 depth, 5-7 rgb_var, 8 depth_var, 9.. semantic logits).
+ * counters: int[4] = {live rays now, live rays collected for the next iteration,
+ *                     samples emitted this iteration, iterations that had work}. */
+
+/* Dataset.generate_image_rays (+ the rounded-linspace subsample) --
+ * perception/data_proc/habitat_to_data.py:274-301, 461-467.  c2w [n_views,3,4] f32;
+ * keep_idx int32 [n_keep] pixel indices (NULL = all width*height pixels, n_keep must match). */
+int apnerf_generate_rays(int n_views, const float* c2w, int width, int height, float focal, int n_keep,
+                         const int* keep_idx, float* rays_o, float* rays_d, void* stream);
+
+/* utils.py:860-892: zero the state, ray/aabb intersection, every ray live. */
+int apnerf_render_init(int n_rays, int rays_per_call, const float* rays_o, const float* rays_d, int rx,
+                       int ry, int rz, const uint8_t* binaries, const float* aabbs, float near_plane,
+                       int n_state, float* state, float* t_min, float* t_max, uint8_t* hit, float* near,
+                       int* alive, int* n_alive_acc, int* iter_samples, int* total_samples, int n_calls,
+                       int* counters, void* stream);
+/* utils.py:896-903: per call n = max(min(R // n_alive, 64), min_samples), iter_samples += n. */
+int apnerf_render_schedule(int n_calls, int rays_per_call, int max_samples, int min_samples,
+                           int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, void* stream);
+/* utils.py:906-929: limited traversal of every live ray from its last terminate plane;
+ * emits the compact sample list (s_ray, s_ts, s_te), counters[2] and per-entry (base, count). */
+int apnerf_render_march(int max_live, int rays_per_call, const int* alive, const int* n_samp,
+                        const float* rays_o, const float* rays_d, int rx, int ry, int rz,
+                        const uint8_t* binaries, const float* aabbs, const float* t_min, const float* t_max,
+                        const uint8_t* hit, float* near, float far_plane, float step_size, float cone_angle,
+                        int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
+                        int* counters, void* stream);
+/* utils.py:937-1009: weights with prefix transmittance, alpha_thre filter, accumulation, variance
+ * terms, next ray mask, live-list compaction.  dens [s], rgb_s [3][s_cap], sem_s [n_sem][s_cap]. */
+int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem, long long s_cap,
+                            const int* alive, const int* entry_base, const int* entry_cnt,
+                            const float* s_ts, const float* s_te, const float* dens, const float* rgb_s,
+                            const float* sem_s, float* state, float alpha_thre, float opc_thre,
+                            const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
+                            int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
+                            void* stream);
+/* utils.py:1012-1032: background, depth normalisation, [n_rays, D] outputs (any may be NULL). */
+int apnerf_render_finalize(int n_rays, int n_sem, const float* state, float bkgd_r, float bkgd_g,
+                           float bkgd_b, float* rgb, float* rgb_var, float* opacity, float* depth,
+                           float* depth_var, float* sem, void* stream);
+/* ActiveNeRFMapper.probablistic_uncertainty arithmetic -- scripts/pipeline.py:727-781.
+ * state0..3: per-member state arrays (unused ones NULL); view_traj int32 [n_views] maps a view to
+ * its trajectory (-1 = skip); sums double [n_traj][4] += per-pixel (rgb, depth, sem, occ) terms. */
+int apnerf_score_views(int n_members, const float* state0, const float* state1, const float* state2,
+                       const float* state3, int n_rays, int rays_per_view, int n_sem,
+                       const int* view_traj, int n_traj, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

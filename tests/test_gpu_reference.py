@@ -75,7 +75,10 @@ def test_traverse_train_mode_bit_exact(apnerf, ref_cuda, oracle, n_grids, res, s
     _same(iv.is_right, riv.is_right, "is_right")
     _same(iv.ray_indices, riv.ray_indices, "interval ray_indices")
     _same(iv.packed_info[:, 1], riv.chunk_cnts, "interval counts")
-    _same(term, rterm, "terminate planes")
+    # rays without samples are skipped by the fill pass (grid.cu:103-106): their terminate plane is
+    # uninitialised memory (torch::empty) in the reference, so only rays with samples are compared
+    has = rsm.chunk_cnts > 0
+    _same(term[has], rterm[has], "terminate planes")
     # ... and the C oracle agrees with the reference kernel too (this is what pins the oracle)
     t_sorted, t_indices, hits = (t.cpu().numpy() for t in isect)
     oiv, osm, oterm = oracle.traverse_grids(rays_o.cpu().numpy(), rays_d.cpu().numpy(), binaries.cpu().numpy(),
@@ -83,7 +86,8 @@ def test_traverse_train_mode_bit_exact(apnerf, ref_cuda, oracle, n_grids, res, s
                                             cone, t_sorted=t_sorted, t_indices=t_indices, hits=hits)
     assert (osm["chunk_cnts"] == rsm.chunk_cnts.cpu().numpy()).all()
     assert (oiv["vals"].view(np.int32) == riv.vals.cpu().numpy().view(np.int32)).all()
-    assert (oterm.view(np.int32) == rterm.cpu().numpy().view(np.int32)).all()
+    has = has.cpu().numpy()
+    assert (oterm.view(np.int32)[has] == rterm.cpu().numpy().view(np.int32)[has]).all()
 
 
 @pytest.mark.parametrize("limit,cone", [(4, 0.004), (64, 0.004), (7, 0.0)])
