@@ -68,14 +68,15 @@ APNERF_API int apnerf_hashgrid_encode(long long n, const float* x01, int n_level
 
 // Fused field query.  Exactly one of {positions(+directions)} / {ray_idx, t_starts, t_ends,
 // rays_o, rays_d} describes the sample points.  n_dev (optional, device int32) overrides n.
-// Outputs: density [n]; rgb / sem element (i, c) at base[c * ch_stride + i * row_stride].
+// Outputs: density [n]; rgb / sem element (i, c) at base[c * ch_stride + i * row_stride]; or, when
+// `packed` is given, one 80-byte row of raw fp16 network outputs per sample (fused renderer).
 APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* positions, const float* directions,
                                     const int* ray_idx, const float* t_starts, const float* t_ends,
                                     const float* rays_o, const float* rays_d, const float* aabb_host,
                                     int n_levels, const uint32_t* meta_host, const void* table,
                                     const void* weights, float* density, float* rgb, long long rgb_row,
                                     long long rgb_ch, float* sem, long long sem_row, long long sem_ch, int n_sem,
-                                    void* feat, int density_only, long long max_tiles, void* stream) {
+                                    void* feat, void* packed, int density_only, long long max_tiles, void* stream) {
   if (n == 0 && n_dev == nullptr) return 0;
   APNERF_REQUIRE(positions != nullptr || ray_idx != nullptr, "field_forward: no sample points given");
   APNERF_REQUIRE(density_only || positions == nullptr || directions != nullptr, "field_forward: directions missing");
@@ -92,6 +93,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   io.density = density, io.rgb = rgb, io.rgb_row = rgb_row, io.rgb_ch = rgb_ch;
   io.sem = sem, io.sem_row = sem_row, io.sem_ch = sem_ch, io.feat = (__half*)feat, io.n_sem = sem ? n_sem : 0;
   io.density_only = density_only;
+  io.packed = (uint4*)packed;
   HashGridMeta m;
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward: bad level table");
   FieldConst fc;

@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(256) render_march_kernel(const int* counters_i
 // (utils.py:957-999), next ray mask (utils.py:1004-1009) and compaction of the live list.
 template <bool PROB>
 __global__ void __launch_bounds__(128) render_composite_kernel(
-    const int* counters_in, int n_rays, int rays_per_call, int n_sem, long long s_cap,
+    const int* counters_in, int n_rays, int rays_per_call, int n_sem,
     const int* __restrict__ alive, const int* __restrict__ entry_base, const int* __restrict__ entry_cnt,
-    const float* __restrict__ s_ts, const float* __restrict__ s_te, const float* __restrict__ dens,
-    const float* __restrict__ rgb_s, const float* __restrict__ sem_s, float* __restrict__ state, float alpha_thre,
+    const float* __restrict__ s_ts, const float* __restrict__ s_te, const uint4* __restrict__ rows,
+    float* __restrict__ state, float alpha_thre,
     float opc_thre, const int* __restrict__ n_samp, const int* __restrict__ iter_samples, int max_samples,
     int* __restrict__ alive_next, int* __restrict__ n_alive_acc, int* __restrict__ total_samples,
     int* counters) {
@@ -209,7 +209,11 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
         for (int j = 0; j < k; ++j) {
           const int s = base + j;
           const float t0 = s_ts[s], t1 = s_te[s];
-          const float sdt = __fmul_rn(dens[s], __fsub_rn(t1, t0));
+          __align__(16) __half h[40];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) reinterpret_cast<uint4*>(h)[q] = __ldg(rows + (size_t)s * 5 + q);
+          const float sigma = expf(__fsub_rn(__half2float(h[0]), 1.0f));  // exp(-inf) = 0 outside the aabb
+          const float sdt = __fmul_rn(sigma, __fsub_rn(t1, t0));
           const float alpha = __fsub_rn(1.0f, expf(-sdt));
           const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
           esum = __fadd_rn(esum, sdt);
@@ -217,12 +221,15 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
           ++n_vis;
           const float tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) rgb[c] = __fadd_rn(rgb[c], __fmul_rn(w, rgb_s[c * s_cap + s]));
+          for (int c = 0; c < 3; ++c) {
+            const float col = 1.0f / (1.0f + expf(-__half2float(h[1 + c])));
+            rgb[c] = __fadd_rn(rgb[c], __fmul_rn(w, col));
+          }
           opac = __fadd_rn(opac, w);
           depth = __fadd_rn(depth, __fmul_rn(w, tmid));
 #pragma unroll
           for (int c = 0; c < 32; ++c)
-            if (c < n_sem) sem[c] = __fadd_rn(sem[c], __fmul_rn(w, sem_s[c * s_cap + s]));
+            if (c < n_sem) sem[c] = __fadd_rn(sem[c], __fmul_rn(w, __half2float(h[4 + c])));
         }
         if (PROB) {
           float rv[3] = {st[ST_RGBVAR * NR], st[(ST_RGBVAR + 1) * NR], st[(ST_RGBVAR + 2) * NR]};
@@ -231,7 +238,10 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
           for (int j = 0; j < k; ++j) {
             const int s = base + j;
             const float t0 = s_ts[s], t1 = s_te[s];
-            const float sdt = __fmul_rn(dens[s], __fsub_rn(t1, t0));
+            const uint4 r0 = __ldg(rows + (size_t)s * 5);
+            const __half* h = reinterpret_cast<const __half*>(&r0);
+            const float sigma = expf(__fsub_rn(__half2float(h[0]), 1.0f));
+            const float sdt = __fmul_rn(sigma, __fsub_rn(t1, t0));
             const float alpha = __fsub_rn(1.0f, expf(-sdt));
             const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
             esum = __fadd_rn(esum, sdt);
@@ -239,7 +249,8 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
             const float tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float df = __fsub_rn(rgb_s[c * s_cap + s], rgb[c]);
+              const float col = 1.0f / (1.0f + expf(-__half2float(h[1 + c])));
+              const float df = __fsub_rn(col, rgb[c]);
               rv[c] = __fadd_rn(rv[c], __fmul_rn(w, __fmul_rn(df, df)));
             }
             const float dd = __fsub_rn(tmid, depth);
@@ -440,10 +451,10 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
   return 0;
 }
 
-APNERF_API int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem, long long s_cap,
+APNERF_API int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem,
                                        const int* alive, const int* entry_base, const int* entry_cnt,
-                                       const float* s_ts, const float* s_te, const float* dens, const float* rgb_s,
-                                       const float* sem_s, float* state, float alpha_thre, float opc_thre,
+                                       const float* s_ts, const float* s_te, const void* rows, float* state,
+                                       float alpha_thre, float opc_thre,
                                        const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
                                        int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
                                        void* stream) {
@@ -452,11 +463,11 @@ APNERF_API int apnerf_render_composite(int max_live, int n_rays, int rays_per_ca
   const int grid = grid_for(max_live, 128, 16);
   if (probabilistic)
     render_composite_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
-        counters, n_rays, rays_per_call, n_sem, s_cap, alive, entry_base, entry_cnt, s_ts, s_te, dens, rgb_s, sem_s,
+        counters, n_rays, rays_per_call, n_sem, alive, entry_base, entry_cnt, s_ts, s_te, (const uint4*)rows,
         state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters);
   else
     render_composite_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
-        counters, n_rays, rays_per_call, n_sem, s_cap, alive, entry_base, entry_cnt, s_ts, s_te, dens, rgb_s, sem_s,
+        counters, n_rays, rays_per_call, n_sem, alive, entry_base, entry_cnt, s_ts, s_te, (const uint4*)rows,
         state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters);
   APNERF_CHECK_LAUNCH("render_composite_kernel");
   return 0;

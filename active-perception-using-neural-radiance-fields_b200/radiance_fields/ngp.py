@@ -206,7 +206,7 @@ class NGPRadianceField(torch.nn.Module):
                 call("apnerf_field_forward", n, None, pos, dirs, None, None, None, None, None,
                      aabb_host.ctypes.data_as(ctypes.c_void_p), self.n_levels,
                      self._meta.ctypes.data_as(ctypes.c_void_p), table, weights, density,
-                     rgb, 3, 1, sem, C, 1, C, feat, 1 if density_only else 0, 0)
+                     rgb, 3, 1, sem, C, 1, C, feat, None, 1 if density_only else 0, 0)
         return density, rgb, sem, feat
 
     def _apply(self, fn, *a, **k):

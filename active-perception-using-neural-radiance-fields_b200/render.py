@@ -70,9 +70,7 @@ class FusedRenderer:
             self.s_ray = torch.empty(s_cap, device=dev, dtype=torch.int32)
             self.s_ts = torch.empty(s_cap, device=dev)
             self.s_te = torch.empty(s_cap, device=dev)
-            self.dens = torch.empty(s_cap, device=dev)
-            self.rgb_s = torch.empty((3, s_cap), device=dev)
-            self.sem_s = torch.empty((max(self.n_sem, 1), s_cap), device=dev)
+            self.rows = torch.empty((s_cap, 40), device=dev, dtype=torch.float16)  # raw fp16 network outputs
             self._cap_samples = s_cap
         if n_calls > self._cap_calls:
             self.n_alive_acc = torch.empty(n_calls, device=dev, dtype=torch.int32)
@@ -134,10 +132,10 @@ class FusedRenderer:
                     debug_hook(it, self)
                 call("apnerf_field_forward", 0, self.counters[2:3], None, None, self.s_ray, self.s_ts, self.s_te,
                      rays_o, rays_d, aabb_host.ctypes.data_as(ctypes.c_void_p), radiance_field.n_levels,
-                     meta.ctypes.data_as(ctypes.c_void_p), table, weights, self.dens, self.rgb_s, 1, s_cap,
-                     self.sem_s if self.n_sem else None, 1, s_cap, self.n_sem, None, 0, (s_cap + 127) // 128)
-                call("apnerf_render_composite", n_rays, n_rays, rays_per_call, self.n_sem, s_cap, cur,
-                     self.entry_base, self.entry_cnt, self.s_ts, self.s_te, self.dens, self.rgb_s, self.sem_s, state,
+                     meta.ctypes.data_as(ctypes.c_void_p), table, weights, None, None, 0, 0, None, 0, 0,
+                     self.n_sem, None, self.rows, 0, (s_cap + 127) // 128)
+                call("apnerf_render_composite", n_rays, n_rays, rays_per_call, self.n_sem, cur,
+                     self.entry_base, self.entry_cnt, self.s_ts, self.s_te, self.rows, state,
                      float(alpha_thre), opc_thre, self.n_samp, self.iter_samples, int(max_samples), nxt,
                      self.n_alive_acc, self.total_samples, self.counters, 1 if probabilistic else 0)
                 if poll_every and (it + 1) % poll_every == 0:

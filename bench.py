@@ -51,11 +51,18 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.lines, self.proc, self.index = [], None, index
+        self.lo = self.hi = None
+
+    def mark_begin(self):
+        self.lo = len(self.lines)
+
+    def mark_end(self):
+        self.hi = len(self.lines)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except Exception:
@@ -66,7 +73,12 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        lines = self.lines[self.lo:self.hi] if self.lo is not None else self.lines
+        window = "timed region"
+        if len(lines) < 3:  # region shorter than a few sampling periods: use everything since warm-up began
+            lines, window = self.lines, "warm-up + timed region + e2e (timed region < 3 samples)"
+        self.window = window
+        for l in lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
                 continue
@@ -78,7 +90,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": self.window}
 
 
 # ------------------------------------------------------------------------------------------
@@ -203,12 +215,13 @@ def run_ours(args):
     def step_e2e():
         return scorer.score_views(poses_all, view_traj_all, n_traj)
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler.mark_begin()
     _lib.LAUNCHES.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -216,9 +229,9 @@ def run_ours(args):
         step_device()
     e1.record()
     barrier()
+    sampler.mark_end()
     launches = _lib.kernel_launches()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     # end to end through the public API (host poses in, host scores out)
     step_e2e()
     barrier()
@@ -227,6 +240,7 @@ def run_ours(args):
         terms = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
     tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -318,7 +332,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--views-per-gpu", type=int, default=32)

@@ -114,14 +114,17 @@ int apnerf_hashgrid_encode(long long n, const float* x01, int n_levels, const ui
  * (device int32, may be NULL) overrides n for device-driven loops; max_tiles then bounds the
  * grid.  aabb_host: HOST float[6].  weights: fp16 blob of apnerf_field_weight_bytes() bytes in
  * UMMA K-major layout (see csrc/field.cuh).  Outputs: density [n]; rgb(i,c) at
- * rgb[c*rgb_ch + i*rgb_row]; sem(i,c) likewise for c < n_sem; feat fp16 [n,15] (NULL ok). */
+ * rgb[c*rgb_ch + i*rgb_row]; sem(i,c) likewise for c < n_sem; feat fp16 [n,15] (NULL ok).
+ * packed (NULL ok): instead of density/rgb/sem, write one 80-byte row of 40 fp16 per sample
+ * {density logit (-inf outside the aabb), 3 rgb logits, 32 semantic logits, 4 pad} -- the raw
+ * fp16 network outputs the fused renderer's compositing kernel activates itself. */
 int apnerf_field_forward(long long n, const int* n_dev, const float* positions, const float* directions,
                          const int* ray_idx, const float* t_starts, const float* t_ends,
                          const float* rays_o, const float* rays_d, const float* aabb_host,
                          int n_levels, const uint32_t* meta_host, const void* table,
                          const void* weights, float* density, float* rgb, long long rgb_row,
                          long long rgb_ch, float* sem, long long sem_row, long long sem_ch, int n_sem,
-                         void* feat, int density_only, long long max_tiles, void* stream);
+                         void* feat, void* packed, int density_only, long long max_tiles, void* stream);
 int apnerf_field_weight_bytes(void);
 
 /* ---- the device-driven test-mode renderer + scorer (kernels 1, 4, 5 fused) -------------
@@ -157,11 +160,11 @@ int apnerf_render_march(int max_live, int rays_per_call, const int* alive, const
                         int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
                         int* counters, void* stream);
 /* utils.py:937-1009: weights with prefix transmittance, alpha_thre filter, accumulation, variance
- * terms, next ray mask, live-list compaction.  dens [s], rgb_s [3][s_cap], sem_s [n_sem][s_cap]. */
-int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem, long long s_cap,
+ * terms, next ray mask, live-list compaction.  rows: the field kernel's packed fp16 rows
+ * [s][40]; density = exp(logit - 1) (ngp.py:79), rgb = sigmoid(logit) (ngp.py:211-212). */
+int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem,
                             const int* alive, const int* entry_base, const int* entry_cnt,
-                            const float* s_ts, const float* s_te, const float* dens, const float* rgb_s,
-                            const float* sem_s, float* state, float alpha_thre, float opc_thre,
+                            const float* s_ts, const float* s_te, const void* rows, float* state, float alpha_thre, float opc_thre,
                             const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
                             int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
                             void* stream);
