@@ -1,12 +1,11 @@
 // The fused radiance-field kernel (kernels 2 + 3): hash-grid gather -> base MLP -> {colour head,
 // semantic head}, 128 samples per tile, persistent CTAs (one per SM), warp-specialised:
 //
-//   warps 0-3   epilogue    thread r <-> sample row r <-> TMEM lane r: TMEM -> registers
+//   warps 0-7   epilogue    thread r <-> sample row r <-> TMEM lane r: TMEM -> registers
 //                           (tcgen05.ld), ReLU, fp16, next layer's A operand -> shared memory;
 //                           SH-4 of the view direction; final activations and output.
-//   warp  4     MMA issuer  one thread issues every tcgen05.mma / tcgen05.commit; owns TMEM.
-//   warps 5-12  encoders    256 threads (8 levels of one sample each, 32 gathers in flight per
-//                           thread): 8-byte hash-table gathers (L2-resident table),
+//   warps 8-9   MMA issuers one thread per chain issues tcgen05.mma / tcgen05.commit; warp 8 owns TMEM.
+//   warps 10-25 encoders    512 threads (4 levels of one sample each): 8-byte hash-table gathers (L2-resident table),
 //                           trilinear blend, fp16 features straight into the MMA's A tile.
 //
 // The 64-wide encoding and all activations stay in shared memory / TMEM; only positions come
@@ -26,10 +25,10 @@ namespace apnerf {
 // layer's accumulators, chain 1's MMAs run (ncu on the single-chain version: encoders and the
 // serial MMA -> epilogue chain were both ~90 % busy at ~14.7 k cycles per tile).
 constexpr int N_CHAINS = 2;
-constexpr int N_EPI_WARPS = 4 * N_CHAINS, N_MMA_WARPS = N_CHAINS, N_ENC_WARPS = 8;
-constexpr int FIELD_THREADS = (N_EPI_WARPS + N_MMA_WARPS + N_ENC_WARPS) * 32;  // 576
-constexpr int N_ENC_THREADS = N_ENC_WARPS * 32;                                // 256
-constexpr int LEVELS_PER_ENC_THREAD = MAX_LEVELS * TILE_M / N_ENC_THREADS;     // 8
+constexpr int N_EPI_WARPS = 4 * N_CHAINS, N_MMA_WARPS = N_CHAINS, N_ENC_WARPS = 16;
+constexpr int FIELD_THREADS = (N_EPI_WARPS + N_MMA_WARPS + N_ENC_WARPS) * 32;  // 832
+constexpr int N_ENC_THREADS = N_ENC_WARPS * 32;                                // 512
+constexpr int LEVELS_PER_ENC_THREAD = MAX_LEVELS * TILE_M / N_ENC_THREADS;     // 4
 constexpr int A0_STAGES = 3;
 
 // shared-memory map (bytes).  Per chain ONE 32 KB activation region is reused by every layer:
@@ -174,7 +173,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
   if (warp >= N_EPI_WARPS + N_MMA_WARPS) {
     // =============================== encoders ===============================
     const int e = threadIdx.x - (N_EPI_WARPS + N_MMA_WARPS) * 32;
-    const int row = e & (TILE_M - 1), part = e >> 7;  // this thread does levels [8*part, 8*part+8)
+    const int row = e & (TILE_M - 1), part = e >> 7;  // this thread does levels [4*part, 4*part+4)
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it % A0_STAGES;
@@ -193,7 +192,10 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       for (int j = 0; j < LEVELS_PER_ENC_THREAD / 2; ++j) {
         const int l = part * LEVELS_PER_ENC_THREAD + 2 * j;
         uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-        if (valid) encode_level_pair(meta, l, x, io.table, lo, hi);  // 16 gathers in flight
+        if (valid) {
+          if (l < meta.n_levels) lo = encode_level(meta, l, x, io.table);
+          if (l + 1 < meta.n_levels) hi = encode_level(meta, l + 1, x, io.table);
+        }
         q[j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
       }
       ptx::mbar_wait(bar_empty + 8 * buf, ph ^ 1);  // MMA of the tile that used this slot is done
