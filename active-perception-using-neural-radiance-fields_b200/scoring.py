@@ -156,10 +156,19 @@ class PredictiveInformationScorer:
         sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
         if hi > lo:
             self.partial_sums(c2w, vt, n_traj, sums)
-        if use_dist and world > 1:
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=process_group)
+        sums = all_reduce_partial_sums(sums, process_group)
         counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
         return self.finish(sums.cpu().numpy(), counts)
+
+
+def all_reduce_partial_sums(sums: torch.Tensor, process_group=None) -> torch.Tensor:
+    """The ONE collective of the render + score path: sum the per-rank [n_traj, 4] float64 partial
+    sums (NCCL over NVLink on GPUs; any torch.distributed backend works)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=process_group)
+    return sums
 
 
 def shard_range(n: int, rank: int, world: int):

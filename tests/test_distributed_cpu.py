@@ -1,0 +1,84 @@
+"""CPU, world_size 2, gloo: the multi-rank host logic of the scorer -- contiguous view sharding,
+per-trajectory partial sums, the single all-reduce, the final normalisation -- gives the same
+scores as one rank.  (The per-pixel terms come from the oracle here; the GPU kernels are
+covered by the -m gpu tests.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pixel_terms(rgb_var, depth_var, acc, sem):
+    """Per-view sums of the four per-pixel predictive-information terms (float64), from the oracle
+    formulas: sums over views/pixels are linear, which is what makes view sharding exact."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+
+    V = rgb_var.shape[1]
+    out = np.zeros((V, 4))
+    for v in range(V):
+        t = O.predictive_information(rgb_var[:, v:v + 1], depth_var[:, v:v + 1], acc[:, v:v + 1], sem[:, v:v + 1])
+        n = rgb_var.shape[2]
+        out[v] = [t[0] * n * 3, t[1] * n, t[2] / 3 * n, t[3] / 2 * n]  # undo the means / weights -> sums
+    return out
+
+
+def _worker(rank, world, port, poses_n, view_traj, per_view, n_traj, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import all_reduce_partial_sums, shard_range
+
+    lo, hi = shard_range(poses_n, rank, world)
+    sums = torch.zeros((n_traj, 4), dtype=torch.float64)
+    for v in range(lo, hi):
+        sums[view_traj[v]] += torch.from_numpy(per_view[v])
+    sums = all_reduce_partial_sums(sums)
+    if rank == 0:
+        ret.put(sums.numpy())
+    dist.destroy_process_group()
+
+
+def test_view_sharding_world2_matches_single_rank():
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import PredictiveInformationScorer, shard_range
+
+    rng = np.random.default_rng(0)
+    E, V, P, C, T = 2, 7, 50, 29, 3
+    rgb_var = rng.random((E, V, P, 3)) * 0.02
+    depth_var = rng.random((E, V, P)) * 0.3
+    acc = rng.random((E, V, P))
+    sem = rng.standard_normal((E, V, P, C)) * 2
+    view_traj = np.array([0, 0, 0, 1, 1, 2, 2])
+    per_view = _pixel_terms(rgb_var, depth_var, acc, sem)
+    # ranges are contiguous, balanced and cover everything
+    assert [shard_range(7, r, 2) for r in range(2)] == [(0, 4), (4, 7)]
+    assert [shard_range(256, r, 8) for r in range(8)] == [(32 * r, 32 * r + 32) for r in range(8)]
+    assert [shard_range(3, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, V, view_traj, per_view, T, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    sums = ret.get(timeout=120)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    counts = np.bincount(view_traj, minlength=T) * P
+    terms = PredictiveInformationScorer.finish(sums, counts)
+    from oracle import oracle as O
+
+    for t in range(T):
+        sel = view_traj == t
+        ref = O.predictive_information(rgb_var[:, sel], depth_var[:, sel], acc[:, sel], sem[:, sel])
+        assert np.allclose(terms[t], ref, rtol=1e-10, atol=1e-12), (t, terms[t], ref)
