@@ -75,7 +75,7 @@ struct FieldIO {
   long long sem_row, sem_ch;
   __half* feat;                 // optional [n, 15] geo features (query_density(return_feat=True))
   uint4* packed;                // optional [n][5] x 16 B rows of 40 fp16: raw network outputs for the fused
-                                // renderer {density logit (-inf outside the aabb), rgb logits x3, sem logits}
+                                // renderer {density logit (-inf outside the aabb), rgb logits x3, sigma fp32, pad, 32 sem logits}
   int n_sem;                    // number of semantic classes actually written (<= 32), 0 = none
   int density_only;             // stop after the base MLP
 };
@@ -363,10 +363,11 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         row_h[0] = dens_logit;
 #pragma unroll
         for (int c = 0; c < 3; ++c) row_h[1 + c] = __float2half_rn(__uint_as_float(oh[c]));
+        // halves 4-5 carry sigma = exp(logit - 1) * selector as fp32 so the compositor needs no exp for it
+        reinterpret_cast<float*>(row_h)[2] = expf(__fsub_rn(__half2float(dens_logit), 1.0f));
+        row_h[6] = row_h[7] = __ushort_as_half((unsigned short)0);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) row_h[4 + c] = __float2half_rn(__uint_as_float(os[c]));
-#pragma unroll
-        for (int c = 36; c < 40; ++c) row_h[c] = __ushort_as_half((unsigned short)0);
+        for (int c = 0; c < 32; ++c) row_h[8 + c] = __float2half_rn(__uint_as_float(os[c]));
         uint4* dst = io.packed + (size_t)s * 5;
 #pragma unroll
         for (int j = 0; j < 5; ++j) dst[j] = reinterpret_cast<const uint4*>(row_h)[j];

@@ -117,7 +117,7 @@ struct LocalSink {
 // One thread per live ray: march up to n samples from the ray's previous terminate plane and
 // append them to the compact per-iteration sample list (warp-aggregated reservation keeps the
 // samples of neighbouring rays adjacent, which is what gives the hash-grid gather its locality).
-__global__ void __launch_bounds__(256) render_march_kernel(const int* counters_in, int rays_per_call,
+__global__ void __launch_bounds__(128) render_march_kernel(const int* counters_in, int rays_per_call,
                                                            const int* __restrict__ alive, const int* __restrict__ n_samp,
                                                            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                            GridView g, const float* __restrict__ t_min,
@@ -173,9 +173,34 @@ __global__ void __launch_bounds__(256) render_march_kernel(const int* counters_i
 }
 
 // One thread per live ray: transmittance weights of this iteration's samples (prefix = 1 - the
-// accumulated opacity, utils.py:937-944), alpha_thre filter, accumulation of rgb / opacity /
-// depth / semantic logits, then the variance terms against the UPDATED running rgb / depth
+// accumulated opacity, utils.py:937-944), alpha_thre filter, accumulation of rgb / opacity / depth /
+// semantic logits, then the variance terms against the UPDATED running rgb / depth
 // (utils.py:957-999), next ray mask (utils.py:1004-1009) and compaction of the live list.
+// (A 4-lanes-per-ray variant was measured slower: the weights' exp() calls were then issued by every
+// lane and the kernel became MUFU-bound.)  The per-sample weight / colour / midpoint of the first
+// pass are kept in registers for the common case k <= 4 so the variance pass costs no exp().
+// Sample row (40 fp16): [density logit, r, g, b logits, sigma as fp32 (2 halves), 0, 0 | 32 sem logits].
+struct SampleTerms {
+  float w, col[3], tmid;
+  bool vis;
+};
+
+__device__ __forceinline__ SampleTerms sample_terms(const uint4& r0, float t0, float t1, float esum, float prefix,
+                                                    float alpha_thre, float& sdt_out) {
+  SampleTerms o;
+  const __half* h0 = reinterpret_cast<const __half*>(&r0);
+  const float sigma = __uint_as_float(r0.z);  // exp(logit - 1) * selector, computed by the field kernel
+  const float sdt = __fmul_rn(sigma, __fsub_rn(t1, t0));
+  const float alpha = __fsub_rn(1.0f, expf(-sdt));
+  o.w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
+  o.vis = !(alpha_thre > 0.f && !(alpha >= alpha_thre));
+  o.tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o.col[c] = 1.0f / (1.0f + expf(-__half2float(h0[1 + c])));
+  sdt_out = sdt;
+  return o;
+}
+
 template <bool PROB>
 __global__ void __launch_bounds__(128) render_composite_kernel(
     const int* counters_in, int n_rays, int rays_per_call, int n_sem,
@@ -188,6 +213,7 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
   const int n_live = counters_in[0];
   const int lane = threadIdx.x & 31;
   const int n_round = (n_live + 31) & ~31;
+  const size_t NR = (size_t)n_rays;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += blockDim.x * gridDim.x) {
     bool keep = false;
     int ray = -1, call = -1, n_vis = 0;
@@ -196,7 +222,6 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
       call = ray / rays_per_call;
       const int base = entry_base[i], k = entry_cnt[i];
       float* st = state + ray;
-      const size_t NR = (size_t)n_rays;
       float opac = st[ST_OPA * NR];
       if (k > 0) {
         const float prefix = __fsub_rn(1.0f, opac);
@@ -205,56 +230,61 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
         float sem[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) sem[c] = (c < n_sem) ? st[(ST_SEM + c) * NR] : 0.f;
+        SampleTerms cache[4];
         float esum = 0.f;
         for (int j = 0; j < k; ++j) {
           const int s = base + j;
-          const float t0 = s_ts[s], t1 = s_te[s];
-          __align__(16) __half h[40];
-#pragma unroll
-          for (int q = 0; q < 5; ++q) reinterpret_cast<uint4*>(h)[q] = __ldg(rows + (size_t)s * 5 + q);
-          const float sigma = expf(__fsub_rn(__half2float(h[0]), 1.0f));  // exp(-inf) = 0 outside the aabb
-          const float sdt = __fmul_rn(sigma, __fsub_rn(t1, t0));
-          const float alpha = __fsub_rn(1.0f, expf(-sdt));
-          const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
+          const uint4 r0 = __ldg(rows + (size_t)s * 5);
+          float sdt;
+          const SampleTerms tm = sample_terms(r0, s_ts[s], s_te[s], esum, prefix, alpha_thre, sdt);
           esum = __fadd_rn(esum, sdt);
-          if (alpha_thre > 0.f && !(alpha >= alpha_thre)) continue;
-          ++n_vis;
-          const float tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float col = 1.0f / (1.0f + expf(-__half2float(h[1 + c])));
-            rgb[c] = __fadd_rn(rgb[c], __fmul_rn(w, col));
+          if (PROB) {  // static indices only: stays in registers
+            if (j == 0) cache[0] = tm;
+            else if (j == 1) cache[1] = tm;
+            else if (j == 2) cache[2] = tm;
+            else if (j == 3) cache[3] = tm;
           }
-          opac = __fadd_rn(opac, w);
-          depth = __fadd_rn(depth, __fmul_rn(w, tmid));
+          if (!tm.vis) continue;
+          ++n_vis;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rgb[c] = __fadd_rn(rgb[c], __fmul_rn(tm.w, tm.col[c]));
+          opac = __fadd_rn(opac, tm.w);
+          depth = __fadd_rn(depth, __fmul_rn(tm.w, tm.tmid));
+          __align__(16) __half h[32];
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) reinterpret_cast<uint4*>(h)[qd] = __ldg(rows + (size_t)s * 5 + 1 + qd);
 #pragma unroll
           for (int c = 0; c < 32; ++c)
-            if (c < n_sem) sem[c] = __fadd_rn(sem[c], __fmul_rn(w, __half2float(h[4 + c])));
+            if (c < n_sem) sem[c] = __fadd_rn(sem[c], __fmul_rn(tm.w, __half2float(h[c])));
         }
         if (PROB) {
           float rv[3] = {st[ST_RGBVAR * NR], st[(ST_RGBVAR + 1) * NR], st[(ST_RGBVAR + 2) * NR]};
           float dv = st[ST_DVAR * NR];
-          esum = 0.f;
-          for (int j = 0; j < k; ++j) {
-            const int s = base + j;
-            const float t0 = s_ts[s], t1 = s_te[s];
-            const uint4 r0 = __ldg(rows + (size_t)s * 5);
-            const __half* h = reinterpret_cast<const __half*>(&r0);
-            const float sigma = expf(__fsub_rn(__half2float(h[0]), 1.0f));
-            const float sdt = __fmul_rn(sigma, __fsub_rn(t1, t0));
-            const float alpha = __fsub_rn(1.0f, expf(-sdt));
-            const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
-            esum = __fadd_rn(esum, sdt);
-            if (alpha_thre > 0.f && !(alpha >= alpha_thre)) continue;
-            const float tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+          auto add_var = [&](const SampleTerms& tm) {
+            if (!tm.vis) return;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float col = 1.0f / (1.0f + expf(-__half2float(h[1 + c])));
-              const float df = __fsub_rn(col, rgb[c]);
-              rv[c] = __fadd_rn(rv[c], __fmul_rn(w, __fmul_rn(df, df)));
+              const float df = __fsub_rn(tm.col[c], rgb[c]);
+              rv[c] = __fadd_rn(rv[c], __fmul_rn(tm.w, __fmul_rn(df, df)));
             }
-            const float dd = __fsub_rn(tmid, depth);
-            dv = __fadd_rn(dv, __fmul_rn(w, __fmul_rn(dd, dd)));
+            const float dd = __fsub_rn(tm.tmid, depth);
+            dv = __fadd_rn(dv, __fmul_rn(tm.w, __fmul_rn(dd, dd)));
+          };
+          if (k <= 4) {
+            add_var(cache[0]);
+            if (k > 1) add_var(cache[1]);
+            if (k > 2) add_var(cache[2]);
+            if (k > 3) add_var(cache[3]);
+          } else {
+            esum = 0.f;
+            for (int j = 0; j < k; ++j) {
+              const int s = base + j;
+              const uint4 r0 = __ldg(rows + (size_t)s * 5);
+              float sdt;
+              const SampleTerms tm = sample_terms(r0, s_ts[s], s_te[s], esum, prefix, alpha_thre, sdt);
+              esum = __fadd_rn(esum, sdt);
+              add_var(tm);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) st[(ST_RGBVAR + c) * NR] = rv[c];
@@ -334,9 +364,24 @@ __global__ void __launch_bounds__(128) score_views_kernel(int n_members, Ensembl
   for (int i = threadIdx.x; i < n_traj * 4; i += blockDim.x) acc_s[i] = 0.0;
   __syncthreads();
   const size_t NR = (size_t)n_rays;
+  int cur = -1;
+  double a_rgb = 0.0, a_depth = 0.0, a_sem = 0.0, a_occ = 0.0;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      atomicAdd(&acc_s[cur * 4 + 0], a_rgb);
+      atomicAdd(&acc_s[cur * 4 + 1], a_depth);
+      atomicAdd(&acc_s[cur * 4 + 2], a_sem);
+      atomicAdd(&acc_s[cur * 4 + 3], a_occ);
+    }
+    a_rgb = a_depth = a_sem = a_occ = 0.0;
+  };
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += blockDim.x * gridDim.x) {
     const int traj = view_traj[r / rays_per_view];
     if (traj < 0) continue;
+    if (traj != cur) {
+      flush();
+      cur = traj;
+    }
     double t_rgb = 0.0, t_depth, t_sem = 0.0, t_occ;
     for (int c = 0; c < 3; ++c) {
       double vs = 0.0, hs = 0.0;
@@ -390,11 +435,9 @@ __global__ void __launch_bounds__(128) score_views_kernel(int n_members, Ensembl
       }
       t_occ = bern_entropy(as / n_members) - hs / n_members;
     }
-    atomicAdd(&acc_s[traj * 4 + 0], t_rgb);
-    atomicAdd(&acc_s[traj * 4 + 1], t_depth);
-    atomicAdd(&acc_s[traj * 4 + 2], t_sem);
-    atomicAdd(&acc_s[traj * 4 + 3], t_occ);
+    a_rgb += t_rgb, a_depth += t_depth, a_sem += t_sem, a_occ += t_occ;
   }
+  flush();
   __syncthreads();
   for (int i = threadIdx.x; i < n_traj * 4; i += blockDim.x)
     if (acc_s[i] != 0.0) atomicAdd(sums + i, acc_s[i]);
@@ -444,7 +487,7 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
                                    int* counters, void* stream) {
   if (max_live == 0) return 0;
   GridView g{binaries, aabbs, 1, rx, ry, rz};
-  render_march_kernel<<<grid_for(max_live, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+  render_march_kernel<<<grid_for(max_live, 128, 16), 128, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, counters);
   APNERF_CHECK_LAUNCH("render_march_kernel");

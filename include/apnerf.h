@@ -116,7 +116,8 @@ int apnerf_hashgrid_encode(long long n, const float* x01, int n_levels, const ui
  * UMMA K-major layout (see csrc/field.cuh).  Outputs: density [n]; rgb(i,c) at
  * rgb[c*rgb_ch + i*rgb_row]; sem(i,c) likewise for c < n_sem; feat fp16 [n,15] (NULL ok).
  * packed (NULL ok): instead of density/rgb/sem, write one 80-byte row of 40 fp16 per sample
- * {density logit (-inf outside the aabb), 3 rgb logits, 32 semantic logits, 4 pad} -- the raw
+ * {density logit (-inf outside the aabb), 3 rgb logits, sigma = exp(logit - 1) as fp32, 2 pad, 32
+ * semantic logits} -- the raw
  * fp16 network outputs the fused renderer's compositing kernel activates itself. */
 int apnerf_field_forward(long long n, const int* n_dev, const float* positions, const float* directions,
                          const int* ray_idx, const float* t_starts, const float* t_ends,
