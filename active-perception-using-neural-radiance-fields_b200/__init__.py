@@ -4,7 +4,7 @@ A drop-in for the reference's nerfacc ops, NGP radiance field, test-mode rendere
 predictive-information scorer; all device work is hand-written CUDA behind the C-ABI library
 ``libapnerf.so`` (include/apnerf.h).  There is no CPU or PyTorch fallback.
 """
-from . import _lib, nerfacc, radiance_fields, render, scoring, synthetic  # noqa: F401
+from . import _lib, nerfacc, radiance_fields, render, scoring, synthetic, training  # noqa: F401
 from .nerfacc import OccGridEstimator  # noqa: F401
 from .radiance_fields import NGPRadianceField  # noqa: F401
 
@@ -12,6 +12,7 @@ from .render import (  # noqa: F401
     FusedRenderer,
     Rays,
     render_image_with_occgrid_test,
+    render_image_with_occgrid_with_depth_guide,
     render_probablistic_image_with_occgrid_test,
     sem_rendering,
 )
@@ -19,4 +20,4 @@ from .scoring import PredictiveInformationScorer, probablistic_uncertainty  # no
 
 __all__ = ["nerfacc", "radiance_fields", "render", "scoring", "synthetic", "OccGridEstimator", "NGPRadianceField",
            "FusedRenderer", "Rays", "render_image_with_occgrid_test", "render_probablistic_image_with_occgrid_test",
-           "sem_rendering", "PredictiveInformationScorer", "probablistic_uncertainty", "_lib"]
+           "render_image_with_occgrid_with_depth_guide", "sem_rendering", "training", "PredictiveInformationScorer", "probablistic_uncertainty", "_lib"]

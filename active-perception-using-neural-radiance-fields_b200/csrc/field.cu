@@ -29,6 +29,48 @@ __global__ void __launch_bounds__(256) hashgrid_encode_kernel(long long n, const
   }
 }
 
+
+// Backward of the hash-grid interpolation w.r.t. the table: the encoding is linear in the table,
+// d table[corner] += w_corner * d enc[sample, level, :].  One thread per (sample, level); one
+// 16-byte vector atomic per corner into the fp32 gradient of the flat parameter vector
+// (tcnn accumulates grid gradients with atomics as well).
+__global__ void __launch_bounds__(256) hashgrid_encode_bwd_kernel(long long n, const float* __restrict__ x01,
+                                                                  HashGridMeta meta,
+                                                                  const float* __restrict__ d_enc,  // [n, L*4]
+                                                                  float* __restrict__ d_table) {    // [entries, 4]
+  const long long total = n * meta.n_levels;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)blockDim.x * gridDim.x) {
+    const long long s = t / meta.n_levels;
+    const int l = (int)(t % meta.n_levels);
+    const float x[3] = {x01[3 * s], x01[3 * s + 1], x01[3 * s + 2]};
+    const float4 g = *reinterpret_cast<const float4*>(d_enc + s * (meta.n_levels * FEATS) + l * FEATS);
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    uint32_t cell[3];
+    float w[3];
+    level_cell(meta, l, x, cell, w);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float wt = corner_weight(w, c);
+      float4* dst = reinterpret_cast<float4*>(d_table) + corner_index(meta, l, cell, c);
+      atomicAdd(dst, make_float4(wt * g.x, wt * g.y, wt * g.z, wt * g.w));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sh4_kernel(long long n, const float* __restrict__ dirs, __half* __restrict__ out) {
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n; s += (long long)blockDim.x * gridDim.x) {
+    const float d[3] = {dirs[3 * s], dirs[3 * s + 1], dirs[3 * s + 2]};
+    float o[16];
+    sh4(d, o);
+    __align__(16) __half h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = __float2half_rn(o[i]);
+    reinterpret_cast<uint4*>(out + s * 16)[0] = reinterpret_cast<const uint4*>(h)[0];
+    reinterpret_cast<uint4*>(out + s * 16)[1] = reinterpret_cast<const uint4*>(h)[1];
+  }
+}
+
 static int fill_meta(HashGridMeta& m, int n_levels, const uint32_t* meta_host) {
   if (n_levels < 1 || n_levels > MAX_LEVELS) return 1;
   m.n_levels = n_levels;
@@ -63,6 +105,27 @@ APNERF_API int apnerf_hashgrid_encode(long long n, const float* x01, int n_level
   hashgrid_encode_kernel<<<grid_for(n * n_levels, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       n, x01, (const uint2*)table, m, (__half*)out_enc, out_idx);
   APNERF_CHECK_LAUNCH("hashgrid_encode_kernel");
+  return 0;
+}
+
+
+// d_table [entries, 4] fp32 += d enc / d table ^T * d_enc  (d_enc fp32 [n, n_levels*4]).
+APNERF_API int apnerf_hashgrid_encode_bwd(long long n, const float* x01, int n_levels, const uint32_t* meta_host,
+                                          const float* d_enc, float* d_table, void* stream) {
+  if (n == 0) return 0;
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "hashgrid_encode_bwd: bad level table");
+  hashgrid_encode_bwd_kernel<<<grid_for(n * n_levels, 256, 8), 256, 0, (cudaStream_t)stream>>>(n, x01, m, d_enc,
+                                                                                               d_table);
+  APNERF_CHECK_LAUNCH("hashgrid_encode_bwd_kernel");
+  return 0;
+}
+
+// SH degree 4 of unit directions, fp16 [n, 16] (tcnn SphericalHarmonics as used at ngp.py:108-121).
+APNERF_API int apnerf_sh4(long long n, const float* dirs, void* out, void* stream) {
+  if (n == 0) return 0;
+  sh4_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(n, dirs, (__half*)out);
+  APNERF_CHECK_LAUNCH("sh4_kernel");
   return 0;
 }
 

@@ -79,6 +79,66 @@ def _umma_pack(w: torch.Tensor) -> torch.Tensor:
     return w.reshape(n, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
 
 
+class _HashGridEncode(torch.autograd.Function):
+    """fp16 multiresolution hash-grid features of aabb-normalised points, differentiable w.r.t. the
+    fp32 table (CUDA forward ``apnerf_hashgrid_encode``, backward ``apnerf_hashgrid_encode_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, x01, table_f32, meta, n_levels):
+        import ctypes
+
+        x01 = x01.contiguous()
+        n = x01.shape[0]
+        table_h = table_f32.detach().to(torch.float16).contiguous()
+        enc = torch.zeros((n, 64), device=x01.device, dtype=torch.float16)
+        out = enc if n_levels == 16 else torch.empty((n, n_levels * 4), device=x01.device, dtype=torch.float16)
+        if n:
+            with torch.cuda.device(x01.device):
+                call("apnerf_hashgrid_encode", n, x01, n_levels, meta.ctypes.data_as(ctypes.c_void_p), table_h, out,
+                     None)
+        if out is not enc:
+            enc[:, : n_levels * 4] = out
+        ctx.meta, ctx.n_levels, ctx.table_shape = meta, n_levels, table_f32.shape
+        ctx.save_for_backward(x01)
+        return enc.float()  # values are fp16-representable; the graph stays fp32
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+
+        (x01,) = ctx.saved_tensors
+        n = x01.shape[0]
+        d_table = torch.zeros(ctx.table_shape, device=g.device, dtype=torch.float32)
+        g = g[:, : ctx.n_levels * 4].contiguous().float()
+        if n:
+            with torch.cuda.device(g.device):
+                call("apnerf_hashgrid_encode_bwd", n, x01, ctx.n_levels, ctx.meta.ctypes.data_as(ctypes.c_void_p), g,
+                     d_table)
+        return None, d_table, None, None
+
+
+class _HalfLinear(torch.autograd.Function):
+    """y = round_fp16(x_fp16 @ W_fp16^T) with fp32 accumulation (what the fused kernel's tcgen05 layers
+    compute), optional ReLU; backward in fp32 through the rounding (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, x, w, relu):
+        xh, wh = x.to(torch.float16), w.to(torch.float16)
+        y = torch.matmul(xh, wh.t())
+        if relu:
+            y = torch.relu(y)
+        ctx.relu = relu
+        ctx.save_for_backward(xh, wh, y if relu else xh[:0])
+        return y.float()
+
+    @staticmethod
+    def backward(ctx, g):
+        xh, wh, y = ctx.saved_tensors
+        if ctx.relu:
+            g = g * (y > 0)
+        return g @ wh.float(), g.t() @ xh.float(), None
+
+
 class NGPRadianceField(torch.nn.Module):
     """Instant-NGP radiance field with an optional semantic head."""
 
@@ -180,10 +240,8 @@ class NGPRadianceField(torch.nn.Module):
         return self._cache
 
     def _run(self, positions, directions, density_only, return_feat=False):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "NGPRadianceField: the backward pass of the fused field kernel is not built yet; call under "
-                "torch.no_grad() / .eval() (there is no tcnn or PyTorch fallback)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._run_with_grad(positions, directions, density_only, return_feat)
         require_cuda(positions, directions, self.mlp_base.params)
         weights, table = self._packed()
         pos = positions.reshape(-1, 3).to(torch.float32).contiguous()
@@ -208,6 +266,51 @@ class NGPRadianceField(torch.nn.Module):
                      self._meta.ctypes.data_as(ctypes.c_void_p), table, weights, density,
                      rgb, 3, 1, sem, C, 1, C, feat, None, 1 if density_only else 0, 0)
         return density, rgb, sem, feat
+
+    def _split(self, flat, dims):
+        out, o = [], 0
+        for n_out, n_in in dims:
+            out.append(flat[o:o + n_out * n_in].view(n_out, n_in))
+            o += n_out * n_in
+        return out
+
+    def _run_with_grad(self, positions, directions, density_only, return_feat):
+        """Differentiable path (training): the hash-grid gather and its scatter-add backward are the
+        CUDA kernels behind the C-ABI; the small MLPs run as fp16 matmuls with the same rounding points
+        as the fused inference kernel and an fp32 backward.  Gradients reach the flat fp32 ``params``."""
+        require_cuda(positions, directions, self.mlp_base.params)
+        pos = positions.reshape(-1, 3).to(torch.float32)
+        aabb_min, aabb_max = torch.split(self.aabb, 3, dim=-1)
+        x = ((pos - aabb_min) / (aabb_max - aabb_min)).detach()
+        selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
+        w1, w2, w3 = self._split(self.mlp_base.params[: self._n_base_w], self._base_dims)
+        table = self.mlp_base.params[self._n_base_w:].view(-1, 4)
+        enc = _HashGridEncode.apply(x, table, self._meta, self.n_levels)
+        h = _HalfLinear.apply(enc, w1, True)
+        h = _HalfLinear.apply(h, w2, True)
+        base = _HalfLinear.apply(h, w3, False)
+        density = self.density_activation(base[:, :1]) * selector[:, None]
+        feat = base[:, 1:1 + self.geo_feat_dim]
+        if density_only:
+            return density.reshape(-1), None, None, (feat if return_feat else None)
+        n = pos.shape[0]
+        dirs = directions.reshape(-1, 3).to(torch.float32).contiguous()
+        sh = torch.empty((n, 16), device=pos.device, dtype=torch.float16)
+        if n:
+            with torch.cuda.device(pos.device):
+                call("apnerf_sh4", n, dirs, sh)
+        ones = torch.ones((n, 1), device=pos.device, dtype=torch.float32)
+        wh1, wh2, wh3 = self._split(self.mlp_head.params, self._head_dims)
+        hh = _HalfLinear.apply(torch.cat([sh.float(), feat, ones], -1), wh1, True)
+        hh = _HalfLinear.apply(hh, wh2, True)
+        rgb = torch.sigmoid(_HalfLinear.apply(hh, wh3, False)[:, :3])
+        sem = None
+        if self.num_semantic_classes > 0:
+            ws1, ws2, ws3 = self._split(self.mlp_sem.params, self._sem_dims)
+            hs = _HalfLinear.apply(torch.cat([feat, ones], -1), ws1, True)
+            hs = _HalfLinear.apply(hs, ws2, True)
+            sem = _HalfLinear.apply(hs, ws3, False)[:, : self.num_semantic_classes]
+        return density.reshape(-1), rgb, sem, (feat if return_feat else None)
 
     def _apply(self, fn, *a, **k):
         self._cache = None

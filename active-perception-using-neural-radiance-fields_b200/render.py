@@ -382,3 +382,52 @@ def sem_rendering(
     if render_bkgd is not None:
         colors = colors + render_bkgd * (1.0 - opacities)
     return colors, opacities, depths, semantics, extras
+
+
+def render_image_with_occgrid_with_depth_guide(
+    radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays, near_plane: float = 0.0,
+    far_plane: float = 1e10, render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,
+    cone_angle: float = 0.0, alpha_thre: float = 0.0, test_chunk_size: int = 8192,
+    timestamps: Optional[torch.Tensor] = None, depth: Optional[torch.Tensor] = None,
+):
+    """Train-mode render, drop-in for perception/models/utils.py:63-219: occupancy-grid sampling with a
+    no-grad density pre-filter (stratified when training), then a differentiable field query on the
+    surviving samples and packed compositing.  Returns (rgb, opacity, depth[, semantics], n_samples)."""
+    assert timestamps is None, "dnerf timestamps are not part of the pipeline's path"
+    rays, rays_shape, num_rays = _flatten_rays(rays)
+    C = radiance_field.num_semantic_classes
+    results = []
+    chunk = torch.iinfo(torch.int32).max if radiance_field.training else test_chunk_size
+    for i in range(0, num_rays, chunk):
+        chunk_rays = namedtuple_map(lambda r: r[i:i + chunk], rays)
+
+        def positions_of(t_starts, t_ends, ray_indices):
+            t_dirs = chunk_rays.viewdirs[ray_indices]
+            return chunk_rays.origins[ray_indices] + t_dirs * (t_starts + t_ends)[:, None] / 2.0, t_dirs
+
+        def sigma_fn(t_starts, t_ends, ray_indices):
+            return radiance_field.query_density(positions_of(t_starts, t_ends, ray_indices)[0]).squeeze(-1)
+
+        def rgb_sigma_sem_fn(t_starts, t_ends, ray_indices):
+            positions, t_dirs = positions_of(t_starts, t_ends, ray_indices)
+            out = radiance_field(positions, t_dirs)
+            return (out[0], out[1].squeeze(-1)) + tuple(out[2:])
+
+        ray_indices, t_starts, t_ends = estimator.sampling(
+            chunk_rays.origins, chunk_rays.viewdirs, sigma_fn=sigma_fn, near_plane=near_plane, far_plane=far_plane,
+            render_step_size=render_step_size, stratified=radiance_field.training, cone_angle=cone_angle,
+            alpha_thre=alpha_thre, depth=depth)
+        n_chunk = chunk_rays.origins.shape[0]
+        if C > 0:
+            rgb, opacity, dep, semantics, _ = sem_rendering(
+                t_starts, t_ends, ray_indices, n_rays=n_chunk, rgb_sigma_sem_fn=rgb_sigma_sem_fn,
+                render_bkgd=render_bkgd, num_sumantic_classes=C)
+            results.append([rgb, opacity, dep, semantics, len(t_starts)])
+        else:
+            from .nerfacc import rendering
+
+            rgb, opacity, dep, _ = rendering(t_starts, t_ends, ray_indices, n_rays=n_chunk,
+                                             rgb_sigma_fn=rgb_sigma_sem_fn, render_bkgd=render_bkgd)
+            results.append([rgb, opacity, dep, len(t_starts)])
+    cols = [torch.cat(r, dim=0) if isinstance(r[0], torch.Tensor) else sum(r) for r in zip(*results)]
+    return tuple(c.view((*rays_shape[:-1], -1)) if isinstance(c, torch.Tensor) else c for c in cols)

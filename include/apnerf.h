@@ -128,6 +128,15 @@ int apnerf_field_forward(long long n, const int* n_dev, const float* positions, 
                          void* feat, void* packed, int density_only, long long max_tiles, void* stream);
 int apnerf_field_weight_bytes(void);
 
+/* Training side of the hash grid (tcnn HashGrid backward, reached from loss.backward() at
+ * scripts/pipeline.py:518): d_table [entries,4] fp32 += sum over samples/corners of
+ * w_corner * d_enc [n, n_levels*4] fp32 (vector atomics). */
+int apnerf_hashgrid_encode_bwd(long long n, const float* x01, int n_levels, const uint32_t* meta_host,
+                               const float* d_enc, float* d_table, void* stream);
+/* tcnn SphericalHarmonics degree 4 (ngp.py:108-121): dirs [n,3] f32 unit vectors -> fp16 [n,16]. */
+int apnerf_sh4(long long n, const float* dirs, void* out, void* stream);
+
+
 /* ---- the device-driven test-mode renderer + scorer (kernels 1, 4, 5 fused) -------------
  * One "call" = one view through one ensemble member (rays_per_call rays); a batch of calls
  * advances in lock step with the reference's per-call marching schedule

@@ -82,3 +82,35 @@ def test_view_sharding_world2_matches_single_rank():
         sel = view_traj == t
         ref = O.predictive_information(rgb_var[:, sel], depth_var[:, sel], acc[:, sel], sem[:, sel])
         assert np.allclose(terms[t], ref, rtol=1e-10, atol=1e-12), (t, terms[t], ref)
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.training import allreduce_gradients
+
+    m = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        m.weight.fill_(1.0), m.bias.fill_(0.0)
+    m.weight.grad = torch.full_like(m.weight, float(rank + 1))  # rank 0 -> 1, rank 1 -> 2
+    allreduce_gradients(m)  # bias.grad is None on purpose: must become zeros, not crash
+    if rank == 0:
+        ret.put((m.weight.grad.clone().numpy(), m.bias.grad.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_averages():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    wg, bg = ret.get(timeout=120)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert np.allclose(wg, 1.5) and np.allclose(bg, 0.0)

@@ -1,0 +1,184 @@
+"""GPU: the training side of the path (BASELINE.json configs[3]) -- hash-grid backward kernel against
+a numpy scatter of the oracle's own cell indices, the differentiable field against the fused inference
+kernel (same rounding points) and against an fp32 torch restatement for gradients, and a short
+optimisation run of the reference's loss (scripts/pipeline.py:507-532)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+AABB = [-6.4, -0.2, -6.4, 6.4, 12.6, 6.4]
+
+
+def _field(apnerf, seed=2, C=29):
+    from apnerf import synthetic
+
+    f = apnerf.NGPRadianceField(AABB, layers=2, num_semantic_classes=C)
+    synthetic.init_trained_like(f, seed=seed, density_gain=2.0)
+    return f.to(DEV)
+
+
+def test_hashgrid_backward_matches_scatter(apnerf, oracle):
+    from apnerf._lib import call
+    from apnerf.radiance_fields.ngp import hashgrid_levels
+
+    meta, total = hashgrid_levels(16, 16, 4096, 19)
+    g = torch.Generator().manual_seed(3)
+    n = 3000
+    x = torch.rand((n, 3), generator=g)
+    d_enc = torch.randn((n, 64), generator=g)
+    d_table = torch.zeros((total, 4), device=DEV)
+    call("apnerf_hashgrid_encode_bwd", n, x.to(DEV), 16, meta.ctypes.data_as(ctypes.c_void_p), d_enc.to(DEV), d_table)
+    # oracle: the encoding is linear in the table -> gradient = scatter of (corner weight x d_enc)
+    ometa = oracle.hashgrid_meta()[0]
+    _, idx = oracle.hashgrid_encode(x.numpy(), np.zeros((total, 4), np.float16), ometa, want_indices=True)
+    ref = np.zeros((total, 4), np.float64)
+    xs = x.numpy()
+    for l in range(16):
+        scale = ometa[l, 0:1].view(np.float32)[0]
+        pos = (np.float32(scale) * xs + np.float32(0.5)).astype(np.float32)
+        w = pos - np.floor(pos)
+        for c in range(8):
+            wt = np.ones(n, np.float32)
+            for a in range(3):
+                wt = wt * (w[:, a] if (c >> a) & 1 else (np.float32(1.0) - w[:, a]))
+            np.add.at(ref, idx[:, l, c].astype(np.int64), wt[:, None].astype(np.float64) * d_enc.numpy()[:, 4 * l:4 * l + 4])
+    got = d_table.cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    assert (got != 0).sum() > 1000
+
+
+def test_training_forward_matches_inference_kernel(apnerf):
+    f = _field(apnerf)
+    g = torch.Generator().manual_seed(0)
+    lo, hi = torch.tensor(AABB[:3]), torch.tensor(AABB[3:])
+    pos = (lo + (hi - lo) * torch.rand((4000, 3), generator=g)).to(DEV)
+    dirs = torch.randn((4000, 3), generator=g)
+    dirs = (dirs / dirs.norm(dim=-1, keepdim=True)).to(DEV)
+    f.eval()
+    with torch.no_grad():
+        rgb0, dens0, sem0 = f(pos, dirs)
+    f.train()
+    rgb1, dens1, sem1 = f(pos, dirs)  # differentiable path
+    assert rgb1.requires_grad and dens1.requires_grad and sem1.requires_grad
+    # same operands and rounding points; only the fp32 accumulation order inside the GEMMs differs
+    assert (rgb0 - rgb1).abs().max() <= 1e-3
+    assert ((dens0 - dens1).abs() / dens0.clamp_min(1e-6)).quantile(0.999) <= 2e-2
+    assert (sem0 - sem1).abs().quantile(0.999) <= 4e-3
+
+
+def test_field_gradients_match_fp32_reference(apnerf):
+    """Gradients w.r.t. the MLP weights and the hash table against a plain fp32 torch restatement of
+    the same network (the fp16 rounding of the forward pass bounds the agreement: a few per cent)."""
+    from apnerf._lib import call
+    from apnerf.radiance_fields.ngp import hashgrid_levels
+
+    f = _field(apnerf)
+    f.train()
+    g = torch.Generator().manual_seed(1)
+    n = 2048
+    lo, hi = torch.tensor(AABB[:3]), torch.tensor(AABB[3:])
+    pos = (lo + (hi - lo) * torch.rand((n, 3), generator=g)).to(DEV)
+    dirs = torch.randn((n, 3), generator=g)
+    dirs = (dirs / dirs.norm(dim=-1, keepdim=True)).to(DEV)
+    tgt_rgb = torch.rand((n, 3), generator=g).to(DEV)
+    tgt_sem = torch.randint(0, 29, (n,), generator=g).to(DEV)
+
+    def loss_of(rgb, dens, sem):
+        return ((rgb - tgt_rgb) ** 2).mean() + (torch.log1p(dens)).mean() * 0.1 + \
+            torch.nn.functional.cross_entropy(sem, tgt_sem) * 0.5
+
+    rgb, dens, sem = f(pos, dirs)
+    loss_of(rgb, dens, sem).backward()
+    got = {k: p.grad.clone() for k, p in f.named_parameters() if p.grad is not None}
+
+    # fp32 restatement: gather with the kernel's own cell indices, fp32 MLPs, torch autograd
+    meta, total = hashgrid_levels(16, 16, 4096, 19)
+    x = ((pos - lo.to(DEV)) / (hi - lo).to(DEV)).contiguous()
+    idx = torch.empty((n, 16, 8), dtype=torch.int32, device=DEV)
+    call("apnerf_hashgrid_encode", n, x, 16, meta.ctypes.data_as(ctypes.c_void_p),
+         f.mlp_base.params[f._n_base_w:].detach().half().contiguous(), None, idx)
+    base_p = f.mlp_base.params.detach().clone().requires_grad_(True)
+    head_p = f.mlp_head.params.detach().clone().requires_grad_(True)
+    sem_p = f.mlp_sem.params.detach().clone().requires_grad_(True)
+    table = base_p[f._n_base_w:].view(-1, 4)
+    scales = torch.from_numpy(meta[:, 0].copy().view(np.float32)).to(DEV)
+    p_ = scales[None, :, None] * x[:, None, :] + 0.5
+    w = p_ - torch.floor(p_)
+    enc = []
+    for c in range(8):
+        wt = torch.ones((n, 16), device=DEV)
+        for a in range(3):
+            wt = wt * (w[..., a] if (c >> a) & 1 else 1 - w[..., a])
+        enc.append(wt[..., None] * table[idx[:, :, c].long()])
+    enc = sum(enc).reshape(n, 64)
+    w1, w2, w3 = f._split(base_p[: f._n_base_w], f._base_dims)
+    base = torch.relu(torch.relu(enc @ w1.t()) @ w2.t()) @ w3.t()
+    dens_r = torch.exp(base[:, :1] - 1)
+    feat = base[:, 1:16]
+    sh = torch.empty((n, 16), device=DEV, dtype=torch.float16)
+    call("apnerf_sh4", n, dirs.contiguous(), sh)
+    ones = torch.ones((n, 1), device=DEV)
+    wh1, wh2, wh3 = f._split(head_p, f._head_dims)
+    rgb_r = torch.sigmoid((torch.relu(torch.relu(torch.cat([sh.float(), feat, ones], -1) @ wh1.t()) @ wh2.t()) @ wh3.t())[:, :3])
+    ws1, ws2, ws3 = f._split(sem_p, f._sem_dims)
+    sem_r = (torch.relu(torch.relu(torch.cat([feat, ones], -1) @ ws1.t()) @ ws2.t()) @ ws3.t())[:, :29]
+    loss_of(rgb_r, dens_r, sem_r).backward()
+    for name, ref in (("mlp_base.params", base_p.grad), ("mlp_head.params", head_p.grad), ("mlp_sem.params", sem_p.grad)):
+        a, b = got[name], ref
+        cos = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)
+        rel = (a - b).norm() / b.norm()
+        assert cos > 0.995 and rel < 0.1, (name, float(cos), float(rel))
+    assert got["direction_encoding.params"].numel() == 0 if "direction_encoding.params" in got else True
+
+
+def test_training_steps_reduce_loss(apnerf):
+    """A few optimisation steps of the reference loss on one fixed synthetic batch (coherent rays from one
+    origin, like habitat_to_data.py:209-218) must reduce the loss; every parameter gets a gradient."""
+    from apnerf import synthetic, training
+
+    torch.manual_seed(0)
+    est = apnerf.OccGridEstimator(synthetic.ROI_AABB, resolution=128, levels=1)
+    est.binaries = synthetic.make_occupancy(128, seed=1)
+    est.occs = est.binaries.flatten().float() * 0.5  # consistent with the binaries for sampling()'s alpha_thre
+    est = est.to(DEV)
+    f = _field(apnerf, seed=4)
+    opt = torch.optim.Adam(f.parameters(), lr=1e-3, eps=1e-15)  # pipeline.py:173-178
+    g = torch.Generator().manual_seed(4)
+    n = 1024
+    d = torch.randn((n, 3), generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    batch = dict(rays=apnerf.Rays(origins=torch.tensor([0.1, 1.5, -0.2]).expand(n, 3).contiguous().to(DEV), viewdirs=d.to(DEV)),
+                 pixels=torch.rand((n, 3), generator=g).to(DEV), dep=(torch.rand(n, generator=g) * 4 + 0.5).to(DEV),
+                 sem=torch.randint(0, 29, (n,), generator=g).to(DEV), color_bkgd=torch.rand(3, generator=g).to(DEV))
+    losses = []
+    for step in range(40):
+        torch.manual_seed(100)  # same stratified jitter every step: the loss is then a fixed function
+        out = training.training_step(f, est, opt, batch, step=step + 1000, update_occupancy=False)
+        assert out is not None and out["n_samples"] > 0
+        losses.append(out["loss"])
+    assert all(p.grad is not None for p in f.parameters())
+    assert losses[-1] < 0.8 * losses[0], (losses[0], losses[-1])
+
+
+def test_train_mode_render_shapes_and_eval_chunking(apnerf):
+    from apnerf import synthetic
+
+    est = apnerf.OccGridEstimator(synthetic.ROI_AABB, resolution=128, levels=1)
+    est.binaries = synthetic.make_occupancy(128, seed=1)
+    est = est.to(DEV).eval()
+    f = _field(apnerf).eval()
+    g = torch.Generator().manual_seed(0)
+    d = torch.randn((20, 30, 3), generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    rays = apnerf.Rays(origins=torch.tensor([0.1, 1.5, -0.2]).expand(20, 30, 3).contiguous().to(DEV), viewdirs=d.to(DEV))
+    with torch.no_grad():
+        rgb, acc, depth, sem, n = apnerf.render_image_with_occgrid_with_depth_guide(
+            f, est, rays, near_plane=0.1, render_step_size=1e-3, render_bkgd=torch.ones(3, device=DEV),
+            cone_angle=0.004, alpha_thre=0.01, test_chunk_size=256)
+    assert rgb.shape == (20, 30, 3) and acc.shape == (20, 30, 1) and depth.shape == (20, 30, 1)
+    assert sem.shape == (20, 30, 29) and n > 0
+    assert torch.isfinite(rgb).all() and (acc >= 0).all() and (acc <= 1 + 1e-5).all()
