@@ -58,3 +58,22 @@ static inline int grid_for(long long n, int threads, int ctas_per_sm) {
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
 }
+
+// Tuning knobs (environment overrides are for experiments; defaults are the measured best).
+#include <stdlib.h>
+static inline float apnerf_skip_min_steps() {
+  static float v = -1.f;
+  if (v < 0.f) {
+    const char* e = getenv("APNERF_SKIP_MIN");
+    v = e ? (float)atof(e) : 32.f;
+  }
+  return v;
+}
+static inline void apnerf_march_cfg(int& threads, int& ctas_per_sm) {
+  static int t = 0, c = 0;
+  if (t == 0) {
+    const char* e = getenv("APNERF_MARCH_CFG");
+    if (!e || sscanf(e, "%d,%d", &t, &c) != 2) t = 256, c = 4;
+  }
+  threads = t, ctas_per_sm = c;
+}

@@ -209,7 +209,7 @@ APNERF_API int apnerf_traverse_grids(int n_rays, const float* rays_o, const floa
                                      float* terminate_planes, void* stream) {
   if (n_rays == 0) return 0;
   APNERF_REQUIRE(n_grids >= 1 && n_grids <= 8, "traverse_grids: n_grids must be in [1, 8]");
-  GridView g{binaries, aabbs, n_grids, rx, ry, rz};
+  GridView g{binaries, aabbs, n_grids, rx, ry, rz, apnerf_skip_min_steps()};
   Segments iv{iv_vals, iv_ray_indices, iv_is_left, iv_is_right, nullptr, iv_chunk_starts, iv_chunk_cnts};
   Segments sm{sm_vals, sm_ray_indices, nullptr, nullptr, sm_is_valid, sm_chunk_starts, sm_chunk_cnts};
   traverse_kernel<<<grid_for(n_rays, 256, 8), 256, 0, (cudaStream_t)stream>>>(

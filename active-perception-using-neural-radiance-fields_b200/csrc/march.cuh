@@ -16,6 +16,7 @@ struct GridView {
   const float* aabbs;       // [n_grids, 6]
   int n_grids;
   int rx, ry, rz;
+  float skip_min_steps;  // use the closed-form skip only when more than this many steps are expected
 };
 
 __device__ __forceinline__ float calc_dt(float t, float cone, float dt_min) {
@@ -45,6 +46,51 @@ __device__ __forceinline__ bool ray_aabb(const float o[3], const float inv[3], f
   tmin = fmaxf(tmin, rtmin);
   tmax = fminf(tmax, rtmax);
   return true;
+}
+
+
+// Exact closed form of the reference's empty-space skip loop (grid.cu:157-161, 199-203)
+//     while (fma(dt, 0.5, t) < target) t = t + dt;          // every add rounded to nearest
+// Inside one binade a float's bit pattern is its mantissa counter, and adding the same dt always
+// advances it by the same integer `inc` (dt / ulp rounded to nearest; the rounding direction depends
+// only on dt's low bits, not on t), so k steps are `bits(t) + k * inc`.  k is estimated in floating
+// point and then corrected with the loop's own predicate, so the result is bit-identical to running
+// the loop (checked against the reference kernels in tests/test_gpu_reference.py).  Ties (dt's low
+// bits exactly half an ulp), binade crossings and tiny t fall back to single exact steps.
+__device__ __forceinline__ float skip_to(float t, float dt, float target, float min_steps) {
+  if (!(target - t > min_steps * dt)) {  // short skip: the plain loop is cheaper than the closed form
+    while (__fmaf_rn(dt, 0.5f, t) < target) t = __fadd_rn(t, dt);
+    return t;
+  }
+  const float h = dt * 0.5f;  // exact (dt >= step_size is never subnormal here)
+  while (__fmaf_rn(dt, 0.5f, t) < target) {
+    const int tb = __float_as_int(t), db = __float_as_int(dt);
+    const int e = (tb >> 23) & 0xff, ed = (db >> 23) & 0xff;
+    const int s = e - ed;
+    bool jumped = false;
+    if (t > 0.0f && s >= 1 && s <= 23 && e > 24 && e < 0xfe) {
+      const unsigned md = ((unsigned)db & 0x7fffffu) | 0x800000u;
+      const unsigned q = md >> s, rem = md & ((1u << s) - 1u), half = 1u << (s - 1);
+      const unsigned inc = q + (rem > half ? 1u : 0u);
+      if (rem != half && inc > 0u) {
+        const unsigned room = 0x7fffffu - ((unsigned)tb & 0x7fffffu);
+        const int kmax = (int)(room / inc);
+        if (kmax >= 2) {
+          const float ulp = __int_as_float((e - 23) << 23);
+          const float kf = (target - h - t) / ((float)inc * ulp);
+          int k = kf >= (float)kmax ? kmax : (kf <= 0.0f ? 0 : (int)kf);
+          while (k < kmax && __fmaf_rn(dt, 0.5f, __int_as_float(tb + k * (int)inc)) < target) ++k;
+          while (k > 0 && !(__fmaf_rn(dt, 0.5f, __int_as_float(tb + (k - 1) * (int)inc)) < target)) --k;
+          if (k > 0) {
+            t = __int_as_float(tb + k * (int)inc);
+            jumped = true;
+          }
+        }
+      }
+    }
+    if (!jumped) t = __fadd_rn(t, dt);
+  }
+  return t;
 }
 
 // March one ray.  `sink(t_last, t_next, continuous)` is called once per emitted sample, in
@@ -86,7 +132,7 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
         t_last = this_tmin;
       } else {
         const float dt = calc_dt(t_last, cone_angle, step_size);
-        while (__fmaf_rn(dt, 0.5f, t_last) < this_tmin) t_last = __fadd_rn(t_last, dt);
+        t_last = skip_to(t_last, dt, this_tmin, g.skip_min_steps);
       }
     }
 
@@ -124,7 +170,7 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
           t_last = t_traverse;
         } else {
           const float dt = calc_dt(t_last, cone_angle, step_size);
-          while (__fmaf_rn(dt, 0.5f, t_last) < t_traverse) t_last = __fadd_rn(t_last, dt);
+          t_last = skip_to(t_last, dt, t_traverse, g.skip_min_steps);
         }
         continuous = false;
       } else {

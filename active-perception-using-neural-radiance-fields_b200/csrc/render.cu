@@ -117,7 +117,7 @@ struct LocalSink {
 // One thread per live ray: march up to n samples from the ray's previous terminate plane and
 // append them to the compact per-iteration sample list (warp-aggregated reservation keeps the
 // samples of neighbouring rays adjacent, which is what gives the hash-grid gather its locality).
-__global__ void __launch_bounds__(128) render_march_kernel(const int* counters_in, int rays_per_call,
+__global__ void __launch_bounds__(256) render_march_kernel(const int* counters_in, int rays_per_call,
                                                            const int* __restrict__ alive, const int* __restrict__ n_samp,
                                                            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                            GridView g, const float* __restrict__ t_min,
@@ -340,21 +340,23 @@ __global__ void __launch_bounds__(256) render_finalize_kernel(int n_rays, int n_
   }
 }
 
-// Predictive information of an ensemble's renders (scripts/pipeline.py:727-781), per pixel in
-// float64 like the reference's numpy, reduced to four sums per trajectory:
+// Predictive information of an ensemble's renders (scripts/pipeline.py:727-781), reduced to four
+// sums per trajectory:
 //   [0] sum over pixels x 3 channels of  H(ensemble rgb var) - mean_m H(rgb var_m)
 //   [1] sum over pixels of the same for depth
 //   [2] sum over pixels of  H(mean_m softmax) - mean_m H(softmax_m)
 //   [3] sum over pixels of  Hb(mean_m acc) - mean_m Hb(acc_m)
 // The host divides by the element counts and applies the x3 / x2 weights (pipeline.py:772-790).
+// The reference does this in float64 numpy on float32 renders; here the per-pixel entropies use
+// full-precision fp32 logf / expf (<= 2 ulp, i.e. <= ~2e-6 absolute per pixel term, far inside the
+// 1e-3 entropy tolerance) and every accumulation across pixels is float64.
 struct EnsembleStates {
   const float* s[4];
 };
 
-__device__ __forceinline__ double gauss_entropy(double var) { return log(2.0 * M_PI * M_E * var + 1e-4) / 2.0; }
-__device__ __forceinline__ double bern_entropy(double a) {
-  return -(a + 1e-4) * log(a + 1e-4) - (1.0 - a + 1e-4) * log(1.0 - a + 1e-4);
-}
+__device__ __forceinline__ float gauss_entropy(float var) { return 0.5f * logf(17.079468445347132f * var + 1e-4f); }
+__device__ __forceinline__ float plogp(float p) { return (p + 1e-4f) * logf(p + 1e-4f); }
+__device__ __forceinline__ float bern_entropy(float a) { return -plogp(a) - plogp(1.0f - a); }
 
 __global__ void __launch_bounds__(128) score_views_kernel(int n_members, EnsembleStates es, int n_rays,
                                                           int rays_per_view, int n_sem,
@@ -364,6 +366,7 @@ __global__ void __launch_bounds__(128) score_views_kernel(int n_members, Ensembl
   for (int i = threadIdx.x; i < n_traj * 4; i += blockDim.x) acc_s[i] = 0.0;
   __syncthreads();
   const size_t NR = (size_t)n_rays;
+  const float inv_m = 1.0f / (float)n_members;
   int cur = -1;
   double a_rgb = 0.0, a_depth = 0.0, a_sem = 0.0, a_occ = 0.0;
   auto flush = [&]() {
@@ -382,60 +385,72 @@ __global__ void __launch_bounds__(128) score_views_kernel(int n_members, Ensembl
       flush();
       cur = traj;
     }
-    double t_rgb = 0.0, t_depth, t_sem = 0.0, t_occ;
+    float t_rgb = 0.f, t_depth, t_sem = 0.f, t_occ;
     for (int c = 0; c < 3; ++c) {
-      double vs = 0.0, hs = 0.0;
+      float vs = 0.f, hs = 0.f;
       for (int m = 0; m < n_members; ++m) {
-        const double v = (double)es.s[m][(ST_RGBVAR + c) * NR + r];
+        const float v = es.s[m][(ST_RGBVAR + c) * NR + r];
         vs += v;
         hs += gauss_entropy(v);
       }
-      t_rgb += gauss_entropy(vs / 2.0) - hs / n_members;  // pipeline.py:733 hard-codes "/ 2"
+      t_rgb += gauss_entropy(vs * 0.5f) - hs * inv_m;  // pipeline.py:733 hard-codes "/ 2"
     }
     {
-      double vs = 0.0, hs = 0.0;
+      float vs = 0.f, hs = 0.f;
       for (int m = 0; m < n_members; ++m) {
-        const double v = (double)es.s[m][ST_DVAR * NR + r];
+        const float v = es.s[m][ST_DVAR * NR + r];
         vs += v;
         hs += gauss_entropy(v);
       }
-      t_depth = gauss_entropy(vs / 2.0) - hs / n_members;
+      t_depth = gauss_entropy(vs * 0.5f) - hs * inv_m;
     }
     if (n_sem > 0) {
-      double pm[32];
-      for (int c = 0; c < 32; ++c) pm[c] = 0.0;
-      double hs = 0.0;
+      float pm[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) pm[c] = 0.f;
+      float hs = 0.f;
       for (int m = 0; m < n_members; ++m) {
         const float* sp = es.s[m] + ST_SEM * NR + r;
-        double mx = -1e300;
-        for (int c = 0; c < n_sem; ++c) mx = fmax(mx, (double)sp[c * NR]);
-        double den = 0.0;
-        for (int c = 0; c < n_sem; ++c) den += exp((double)sp[c * NR] - mx);
-        double h = 0.0;
-        for (int c = 0; c < n_sem; ++c) {
-          const double p = exp((double)sp[c * NR] - mx) / den;
-          pm[c] += p;
-          h -= (p + 1e-4) * log(p + 1e-4);
+        float lg[32];
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          lg[c] = (c < n_sem) ? sp[c * NR] : -3.0e38f;
+          mx = fmaxf(mx, lg[c]);
         }
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          lg[c] = (c < n_sem) ? expf(lg[c] - mx) : 0.f;
+          den += lg[c];
+        }
+        const float inv_den = 1.0f / den;
+        float h = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < n_sem) {
+            const float p = lg[c] * inv_den;
+            pm[c] += p;
+            h -= plogp(p);
+          }
         hs += h;
       }
-      double he = 0.0;
-      for (int c = 0; c < n_sem; ++c) {
-        const double p = pm[c] / n_members;
-        he -= (p + 1e-4) * log(p + 1e-4);
-      }
-      t_sem = he - hs / n_members;
+      float he = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < n_sem) he -= plogp(pm[c] * inv_m);
+      t_sem = he - hs * inv_m;
     }
     {
-      double as = 0.0, hs = 0.0;
+      float as = 0.f, hs = 0.f;
       for (int m = 0; m < n_members; ++m) {
-        const double a = (double)es.s[m][ST_OPA * NR + r];
+        const float a = es.s[m][ST_OPA * NR + r];
         as += a;
         hs += bern_entropy(a);
       }
-      t_occ = bern_entropy(as / n_members) - hs / n_members;
+      t_occ = bern_entropy(as * inv_m) - hs * inv_m;
     }
-    a_rgb += t_rgb, a_depth += t_depth, a_sem += t_sem, a_occ += t_occ;
+    a_rgb += (double)t_rgb, a_depth += (double)t_depth, a_sem += (double)t_sem, a_occ += (double)t_occ;
   }
   flush();
   __syncthreads();
@@ -463,7 +478,7 @@ APNERF_API int apnerf_render_init(int n_rays, int rays_per_call, const float* ra
                                   int* alive, int* n_alive_acc, int* iter_samples, int* total_samples, int n_calls,
                                   int* counters, void* stream) {
   if (n_rays == 0) return 0;
-  GridView g{binaries, aabbs, 1, rx, ry, rz};
+  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
   render_init_kernel<<<grid_for(n_rays, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       n_rays, rays_per_call, rays_o, rays_d, g, near_plane, n_state, state, t_min, t_max, hit, near, alive,
       n_alive_acc, iter_samples, total_samples, n_calls, counters);
@@ -486,8 +501,10 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
                                    int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
                                    int* counters, void* stream) {
   if (max_live == 0) return 0;
-  GridView g{binaries, aabbs, 1, rx, ry, rz};
-  render_march_kernel<<<grid_for(max_live, 128, 16), 128, 0, (cudaStream_t)stream>>>(
+  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  int mt, mc;
+  apnerf_march_cfg(mt, mc);
+  render_march_kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, counters);
   APNERF_CHECK_LAUNCH("render_march_kernel");

@@ -5,7 +5,8 @@
   schedule is purely geometric and must agree iteration by iteration);
 * rendered outputs on the "trained-like" field: fused == op-by-op == oracle within the
   north-star tolerances (written at each assert);
-* predictive information: float64 on both sides, 1e-9 relative.
+* predictive information: fp32 per-pixel entropies with float64 sums against the float64 oracle,
+  1e-5 absolute on each term (the north star allows 1e-3 on entropy).
 """
 import numpy as np
 import pytest
@@ -163,7 +164,8 @@ def test_predictive_information_matches_oracle(apnerf, oracle):
         ref = oracle.predictive_information(
             np.stack([s[5:8].T for s in st]), np.stack([s[8] for s in st]), np.stack([s[3] for s in st]),
             np.stack([s[9:].T for s in st]))
-        assert np.allclose(terms[t], ref, rtol=1e-9, atol=1e-12), (t, terms[t], ref)
+        # per-pixel entropies in fp32 (<= 2 ulp logf / expf), sums in float64: 1e-5 absolute on the means
+        assert np.abs(terms[t] - ref).max() <= 1e-5, (t, terms[t], ref)
 
 
 def test_score_trajectories_end_to_end(apnerf, oracle):
