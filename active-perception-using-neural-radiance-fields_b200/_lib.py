@@ -106,6 +106,47 @@ class _Lib:
             raise RuntimeError(f"{name} failed (code {rc}): {self.last_error()}")
 
 
+class PreparedCall:
+    """A C-ABI call with its arguments converted once: the per-iteration kernel sequence of the
+    renderer re-launches the same entry points with the same pointers hundreds of times, and the
+    ctypes argument marshalling would otherwise cost more than the small kernels themselves."""
+
+    __slots__ = ("name", "fn", "args", "keep")
+
+    def __init__(self, name, *args):
+        LIB._load()
+        self.name = name
+        self.fn = getattr(LIB._dll, name)
+        conv, keep = [], []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if not a.is_cuda or not a.is_contiguous():
+                    raise RuntimeError(f"{name}: tensor arguments must be contiguous CUDA tensors")
+                keep.append(a)
+                conv.append(ctypes.c_void_p(a.data_ptr()))
+            elif a is None:
+                conv.append(ctypes.c_void_p(0))
+            else:
+                conv.append(a)
+        if len(conv) == len(self.fn.argtypes) - 1:
+            conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self.args, self.keep = tuple(conv), keep
+
+    def __call__(self):
+        if CALL_HOOK is not None:  # measurement hook (bench.py wraps launches in CUDA events)
+            return CALL_HOOK(self)
+        self.invoke()
+
+    def invoke(self):
+        LAUNCHES[self.name] = LAUNCHES.get(self.name, 0) + 1
+        rc = self.fn(*self.args)
+        if rc != 0:
+            raise RuntimeError(f"{self.name} failed (code {rc}): {LIB.last_error()}")
+
+
+CALL_HOOK = None
+
+
 # how many times each C-ABI entry point was invoked (bench.py turns this into kernel launches)
 LAUNCHES = {}
 KERNELS_PER_CALL = {"apnerf_exclusive_scan_i64": 3, "apnerf_pack_info": 5}

@@ -157,6 +157,9 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   io.sem = sem, io.sem_row = sem_row, io.sem_ch = sem_ch, io.feat = (__half*)feat, io.n_sem = sem ? n_sem : 0;
   io.density_only = density_only;
   io.packed = (uint4*)packed;
+  io.state = nullptr, io.n_rays_total = 0, io.rays_per_call = 1, io.alpha_thre = 0.f, io.opc_thre = 0.f;
+  io.n_samp = nullptr, io.iter_samples = nullptr, io.max_samples = 0, io.s_cnt = nullptr, io.keep_flag = nullptr;
+  io.total_samples = nullptr, io.probabilistic = 0;
   HashGridMeta m;
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward: bad level table");
   FieldConst fc;
@@ -171,3 +174,39 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
 }
 
 APNERF_API int apnerf_field_weight_bytes(void) { return W_BYTES; }
+
+// Field query of the device-driven renderer with the compositor fused into the epilogue: sample
+// rows (s_ray, s_cnt, s_ts, s_te; *n_rows_dev rows, a multiple of 128, rays never straddle a tile)
+// -> per-ray state update + keep flags.  Replaces apnerf_field_forward + apnerf_render_composite.
+APNERF_API int apnerf_field_forward_fused(const int* n_rows_dev, long long max_tiles, const int* s_ray,
+                                          const uint8_t* s_cnt, const float* s_ts, const float* s_te,
+                                          const float* rays_o, const float* rays_d, const float* aabb_host,
+                                          int n_levels, const uint32_t* meta_host, const void* table,
+                                          const void* weights, int n_sem, float* state, int n_rays_total,
+                                          int rays_per_call, float alpha_thre, float opc_thre, const int* n_samp,
+                                          const int* iter_samples, int max_samples, uint8_t* keep_flag,
+                                          int* total_samples, int probabilistic, void* stream) {
+  APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward_fused: at most 32 semantic classes");
+  static bool attr_set = false;
+  if (!attr_set) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    attr_set = true;
+  }
+  FieldIO io;
+  memset(&io, 0, sizeof(io));
+  io.n = max_tiles * TILE_M;  // capacity of the row buffers
+  io.n_dev = n_rows_dev, io.ray_idx = s_ray, io.t_starts = s_ts, io.t_ends = s_te, io.rays_o = rays_o, io.rays_d = rays_d;
+  io.table = (const uint2*)table, io.weights = (const uint4*)weights, io.n_sem = n_sem;
+  io.state = state, io.n_rays_total = n_rays_total, io.rays_per_call = rays_per_call, io.alpha_thre = alpha_thre;
+  io.opc_thre = opc_thre, io.n_samp = n_samp, io.iter_samples = iter_samples, io.max_samples = max_samples;
+  io.s_cnt = s_cnt, io.keep_flag = keep_flag, io.total_samples = total_samples, io.probabilistic = probabilistic;
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward_fused: bad level table");
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
+  const int sms = apnerf_num_sms();
+  const int grid = (int)(max_tiles < 1 ? 1 : (max_tiles < sms ? max_tiles : sms));
+  field_forward_kernel<<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  APNERF_CHECK_LAUNCH("field_forward_kernel(fused)");
+  return 0;
+}

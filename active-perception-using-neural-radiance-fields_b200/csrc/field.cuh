@@ -11,6 +11,10 @@
 
 namespace apnerf {
 
+// per-ray running state of the test-mode renderer, structure-of-arrays [channel][ray]
+constexpr int ST_RGB = 0, ST_OPA = 3, ST_DEPTH = 4, ST_RGBVAR = 5, ST_DVAR = 8, ST_SEM = 9;
+constexpr int MAX_ITER_SAMPLES = 64;  // the reference caps n at 64 (utils.py:902)
+
 constexpr int MAX_LEVELS = 16;
 constexpr int FEATS = 4;  // features per level (ngp.py:128)
 

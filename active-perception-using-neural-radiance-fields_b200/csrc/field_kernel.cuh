@@ -42,6 +42,16 @@ constexpr int ACT_BYTES = TILE_M * HID * 2;
 constexpr int ACT_XH = 0, ACT_XS = TILE_M * HEAD_IN * 2, ACT_HH = 0, ACT_HS = TILE_M * HID2 * 2;
 constexpr int SM_BAR = SM_ACT + N_CHAINS * ACT_BYTES;             // mbarriers + tmem base
 constexpr int FIELD_SMEM = SM_BAR + 128;
+// Fused compositing scratch ALIASES the chain's activation region (dead once the last layer's MMA has
+// completed, until the next tile's first epilogue stage): keeping the footprint at 192 KB matters,
+// the rest of the 228 KB is the L1 cache the hash-grid gathers hit 50 % of the time.
+constexpr int ROWBUF_BYTES = 5 * TILE_M * 16;                     // 5 chunks x [128 x 16 B] raw fp16 rows
+constexpr int ACT_ROWBUF = 0;
+constexpr int ACT_FBUF = ACT_ROWBUF + ROWBUF_BYTES;               // [6][128] f32 per-sample terms
+constexpr int ACT_WBUF = ACT_FBUF + 6 * TILE_M * 4;               // [128] f32 sample weights
+constexpr int ACT_CBUF = ACT_WBUF + TILE_M * 4;                   // [128] u8 row codes
+static_assert(ACT_CBUF + TILE_M <= ACT_BYTES, "compositing scratch must fit the activation region");
+static_assert(FIELD_SMEM <= 232448, "field kernel shared memory exceeds 227 KB");
 
 // TMEM column map per chain (fp32 accumulators, 128 lanes, 128 columns, reused layer by layer)
 constexpr uint32_t TM_CHAIN = 128;
@@ -78,6 +88,19 @@ struct FieldIO {
                                 // renderer {density logit (-inf outside the aabb), rgb logits x3, sigma fp32, pad, 32 sem logits}
   int n_sem;                    // number of semantic classes actually written (<= 32), 0 = none
   int density_only;             // stop after the base MLP
+  // --- fused compositing (device-driven renderer): when `state` is set, the epilogue composites each
+  // ray's samples (rows of one tile) into the per-ray state instead of writing per-sample outputs ---
+  float* state;                 // [9 + n_sem][n_rays_total] structure-of-arrays
+  int n_rays_total;
+  int rays_per_call;
+  float alpha_thre, opc_thre;
+  const int* n_samp;            // [n_calls] samples per live ray this iteration
+  const int* iter_samples;      // [n_calls]
+  int max_samples;
+  const uint8_t* s_cnt;         // [n] number of samples of the ray that STARTS at this row, else 0
+  uint8_t* keep_flag;           // [n_rays_total] out: ray stays live for the next iteration
+  int* total_samples;           // [n_calls] composited (alpha_thre-visible) samples
+  int probabilistic;            // accumulate the variance terms
 };
 
 __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bits) {
@@ -131,6 +154,138 @@ __device__ __forceinline__ void sample_point(const FieldIO& io, long long s, flo
   }
 }
 
+
+__device__ __forceinline__ void chain_bar_sync(int chain) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + chain) : "memory");
+}
+
+// Fused compositing of one tile (128 rows = whole rays, never straddling).  Same arithmetic, in the
+// same order, as render_composite_kernel: transmittance weights with prefix = 1 - accumulated opacity
+// (utils.py:937-944), alpha_thre filter, rgb / opacity / depth / semantic accumulation, variance against
+// the UPDATED running rgb / depth (utils.py:957-999), next ray mask (utils.py:1004-1009).
+// Three phases separated by chain-wide named barriers:
+//   A (every row, parallel)  own sample: sigma*dt, alpha, sigmoid colours, midpoint -> shared memory;
+//   B (ray's first row)      the short serial part: exclusive sum of sigma*dt, w = exp(-sum)*prefix*alpha
+//                            (-> wbuf), rgb / opacity / depth sums, variances, state update, keep flag;
+//   C (ray's first min(k,4) rows) semantic logits in four groups of 8 channels.
+// `code` = s_cnt of this row.  All 128 threads of the chain call this.
+struct CompositeSmem {
+  uint8_t* rowbuf;  // 5 chunks x [128 x 16 B] raw fp16 rows (chunk-major)
+  float* wbuf;      // [128] sample weights (-1: filtered by alpha_thre)
+  float* fbuf;      // [6][128] sdt, alpha, tmid, col r, col g, col b
+  uint8_t* cbuf;    // [128] row codes
+};
+
+__device__ __forceinline__ void composite_tile(const FieldIO& io, const CompositeSmem& sm, int chain, int row,
+                                               long long tile_base, int code, float t0, float t1,
+                                               const uint4 (&my_row)[5], int lane) {
+  const size_t NR = (size_t)io.n_rays_total;
+  const bool in_ray = code != 0, leader = in_ray && !(code & 0x80);
+  const int j = leader ? 0 : (code & 0x7f);
+  const int ray = in_ray ? io.ray_idx[tile_base + row] : 0;
+  float* st = io.state + ray;
+  // prefetch this thread's share of the ray state (latency overlaps phase A and the barriers)
+  float opac = 0.f, rgb[3] = {0.f, 0.f, 0.f}, depth = 0.f, rv[3] = {0.f, 0.f, 0.f}, dv = 0.f, acc[8];
+  if (leader) {
+    opac = st[ST_OPA * NR], rgb[0] = st[0], rgb[1] = st[NR], rgb[2] = st[2 * NR], depth = st[ST_DEPTH * NR];
+    if (io.probabilistic)
+      rv[0] = st[ST_RGBVAR * NR], rv[1] = st[(ST_RGBVAR + 1) * NR], rv[2] = st[(ST_RGBVAR + 2) * NR], dv = st[ST_DVAR * NR];
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = (in_ray && j < 4 && 8 * j + c < io.n_sem) ? st[(ST_SEM + 8 * j + c) * NR] : 0.f;
+
+  // ---- phase A (the scratch is free: the previous tile's compositing ended with a chain barrier and this
+  // tile's last MMA, the final reader of the activation region it aliases, has completed)
+#pragma unroll
+  for (int q = 0; q < 5; ++q) *reinterpret_cast<uint4*>(sm.rowbuf + q * (TILE_M * 16) + row * 16) = my_row[q];
+  sm.cbuf[row] = (uint8_t)code;
+  {
+    const __half* h0 = reinterpret_cast<const __half*>(&my_row[0]);
+    const float sdt = __fmul_rn(__uint_as_float(my_row[0].z), __fsub_rn(t1, t0));
+    sm.fbuf[0 * TILE_M + row] = sdt;
+    sm.fbuf[1 * TILE_M + row] = __fsub_rn(1.0f, expf(-sdt));
+    sm.fbuf[2 * TILE_M + row] = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm.fbuf[(3 + c) * TILE_M + row] = 1.0f / (1.0f + expf(-__half2float(h0[1 + c])));
+  }
+  chain_bar_sync(chain);
+  const int k = leader ? code : (in_ray ? (int)sm.cbuf[row - j] : 0);
+
+  // ---- phase B
+  int call = -1, n_vis = 0;
+  if (leader) {
+    call = ray / io.rays_per_call;
+    const float prefix = __fsub_rn(1.0f, opac);
+    float esum = 0.f;
+    for (int i = 0; i < k; ++i) {
+      const int r = row + i;
+      const float alpha = sm.fbuf[1 * TILE_M + r];
+      const float w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
+      esum = __fadd_rn(esum, sm.fbuf[0 * TILE_M + r]);
+      const bool vis = !(io.alpha_thre > 0.f && !(alpha >= io.alpha_thre));
+      sm.wbuf[r] = vis ? w : -1.0f;  // negative marks "filtered out" (weights are >= 0)
+      if (!vis) continue;
+      ++n_vis;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) rgb[c] = __fadd_rn(rgb[c], __fmul_rn(w, sm.fbuf[(3 + c) * TILE_M + r]));
+      opac = __fadd_rn(opac, w);
+      depth = __fadd_rn(depth, __fmul_rn(w, sm.fbuf[2 * TILE_M + r]));
+    }
+    if (io.probabilistic) {
+      for (int i = 0; i < k; ++i) {
+        const int r = row + i;
+        const float w = sm.wbuf[r];
+        if (w < 0.f) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float df = __fsub_rn(sm.fbuf[(3 + c) * TILE_M + r], rgb[c]);
+          rv[c] = __fadd_rn(rv[c], __fmul_rn(w, __fmul_rn(df, df)));
+        }
+        const float dd = __fsub_rn(sm.fbuf[2 * TILE_M + r], depth);
+        dv = __fadd_rn(dv, __fmul_rn(w, __fmul_rn(dd, dd)));
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) st[(ST_RGBVAR + c) * NR] = rv[c];
+      st[ST_DVAR * NR] = dv;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) st[c * NR] = rgb[c];
+    st[ST_OPA * NR] = opac;
+    st[ST_DEPTH * NR] = depth;
+    const int n = io.n_samp[call];
+    const bool keep = (n > 0) && (opac <= io.opc_thre) && (k == n) && (io.iter_samples[call] < io.max_samples);
+    io.keep_flag[ray] = keep ? 1 : 0;
+  }
+  chain_bar_sync(chain);  // weights of every ray of the tile are in wbuf
+  // ---- phase C: group g = 8 channels; rows j < min(k, 4) of the ray take groups j, j + min(k,4), ...
+  if (in_ray && j < 4) {
+    const int stride = k < 1 ? 1 : (k < 4 ? k : 4);
+    const int r0row = row - j;
+#pragma unroll 1
+    for (int g = j; g < 4 && 8 * g < io.n_sem; g += stride) {
+      if (g != j) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = (8 * g + c < io.n_sem) ? st[(ST_SEM + 8 * g + c) * NR] : 0.f;
+      }
+      for (int i = 0; i < k; ++i) {
+        const float w = sm.wbuf[r0row + i];
+        if (w < 0.f) continue;
+        const uint4 rq = *reinterpret_cast<const uint4*>(sm.rowbuf + (1 + g) * (TILE_M * 16) + (r0row + i) * 16);
+        const __half* hq = reinterpret_cast<const __half*>(&rq);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w, __half2float(hq[c])));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (8 * g + c < io.n_sem) st[(ST_SEM + 8 * g + c) * NR] = acc[c];
+    }
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, call);
+  const int vis_sum = __reduce_add_sync(peers, n_vis);
+  if (call >= 0 && vis_sum && lane == __ffs(peers) - 1) atomicAdd(io.total_samples + call, vis_sum);
+  chain_bar_sync(chain);  // every reader of the scratch is done before the next tile's activations overwrite it
+}
+
 __global__ void __launch_bounds__(FIELD_THREADS, 1)
 field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst fc) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -141,7 +296,8 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
                  bar_mma = bar_empty + 8 * A0_STAGES, bar_epi = bar_mma + 8 * N_CHAINS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * A0_STAGES + 2 * N_CHAINS));
 
-  const long long n = io.n_dev ? (long long)*io.n_dev : io.n;
+  long long n = io.n_dev ? (long long)*io.n_dev : io.n;
+  if (io.n_dev && io.n > 0 && n > io.n) n = io.n;  // device-side count clamped to the buffer capacity
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
 
   // ---- one-time setup: weights -> smem, barriers, TMEM ----
@@ -180,7 +336,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       const uint32_t ph = (it / A0_STAGES) & 1;
       const long long s = tile * TILE_M + row;
       float x[3] = {0.5f, 0.5f, 0.5f};
-      const bool valid = s < n;
+      const bool valid = s < n && (io.ray_idx == nullptr || io.ray_idx[s] >= 0);  // padding rows carry ray -1
       if (valid) {
         float p[3], d[3];
         sample_point(io, s, p, d, false);
@@ -273,7 +429,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       if ((it % N_CHAINS) != chain) continue;
       const long long s = tile * TILE_M + row;
-      const bool valid = s < n;
+      const bool valid = s < n && (io.ray_idx == nullptr || io.ray_idx[s] >= 0);
       // the sample's point / direction are fetched now and consumed after two MMA round trips
       float p[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f};
       if (valid) sample_point(io, s, p, d, !io.density_only);
@@ -358,7 +514,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();
       ptx::mbar_arrive(my_epi);  // outputs are in registers: the next tile's layer 1 may overwrite TMEM
-      if (valid && io.packed) {
+      if (io.state != nullptr || (valid && io.packed)) {
         __align__(16) __half row_h[40];
         row_h[0] = dens_logit;
 #pragma unroll
@@ -368,9 +524,23 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         row_h[6] = row_h[7] = __ushort_as_half((unsigned short)0);
 #pragma unroll
         for (int c = 0; c < 32; ++c) row_h[8 + c] = __float2half_rn(__uint_as_float(os[c]));
-        uint4* dst = io.packed + (size_t)s * 5;
+        if (io.state != nullptr) {
+          // ---- fused compositing: the tile's rows are exchanged through shared memory
+          CompositeSmem cs;
+          cs.rowbuf = act + ACT_ROWBUF;  // the last layer's MMA is complete: the activation region is free
+          cs.wbuf = reinterpret_cast<float*>(act + ACT_WBUF);
+          cs.fbuf = reinterpret_cast<float*>(act + ACT_FBUF);
+          cs.cbuf = act + ACT_CBUF;
+          uint4 my_row[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) dst[j] = reinterpret_cast<const uint4*>(row_h)[j];
+          for (int j = 0; j < 5; ++j) my_row[j] = reinterpret_cast<const uint4*>(row_h)[j];
+          composite_tile(io, cs, chain, row, (long long)(tile * TILE_M), valid ? (int)io.s_cnt[s] : 0,
+                         valid ? io.t_starts[s] : 0.f, valid ? io.t_ends[s] : 0.f, my_row, lane);
+        } else {
+          uint4* dst = io.packed + (size_t)s * 5;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) dst[j] = reinterpret_cast<const uint4*>(row_h)[j];
+        }
       } else if (valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {

@@ -15,11 +15,10 @@
 // Per-ray running state lives in HBM as structure-of-arrays [channel][ray]:
 //   0-2 rgb | 3 opacity | 4 depth | 5-7 rgb_var | 8 depth_var | 9.. semantic logits (C)
 #include "march.cuh"
+#include "field.cuh"
 
 namespace apnerf {
 
-constexpr int ST_RGB = 0, ST_OPA = 3, ST_DEPTH = 4, ST_RGBVAR = 5, ST_DVAR = 8, ST_SEM = 9;
-constexpr int MAX_ITER_SAMPLES = 64;  // the reference caps n at 64 (utils.py:902)
 
 // counters[0] live rays this iteration, [1] live rays being collected for the next one,
 // [2] samples emitted this iteration, [3] total iterations executed with work
@@ -41,6 +40,10 @@ __global__ void render_schedule_kernel(int n_calls, int rays_per_call, int max_s
     counters[1] = 0;
     counters[2] = 0;
     if (counters[0] > 0) counters[3] += 1;
+    counters[4] = 0;  // ticket counter of render_compact_kernel
+    counters[6] = 0;  // real (non-padding) samples emitted this iteration
+    counters[7] = (counters[7] + 1) & 0x3fffffff;  // generation tag of render_compact_kernel (never 0 after this)
+    if (counters[7] == 0) counters[7] = 1;
   }
 }
 
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256) render_init_kernel(int n_rays, int rays_p
       iter_samples[c] = 0;
       total_samples[c] = 0;
     }
-    if (threadIdx.x == 0) counters[0] = 0, counters[1] = n_rays, counters[2] = 0, counters[3] = 0;
+    if (threadIdx.x == 0) counters[0] = 0, counters[1] = n_rays, counters[2] = 0, counters[3] = 0, counters[4] = 0;  // [5] (overflow) is sticky: the host clears it
   }
 }
 
@@ -169,6 +172,174 @@ __global__ void __launch_bounds__(256) render_march_kernel(const int* counters_i
         s_te[base + j] = te[j];
       }
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// "v2" marching step of the fused pipeline: the compositor runs inside the field kernel's epilogue,
+// which needs every ray's samples inside ONE 128-row tile.  Each warp therefore reserves a
+// 128-aligned run of rows and places its 32 rays' samples one after the other, starting a new
+// tile whenever a ray would straddle a tile boundary; unused rows are marked ray = -1.
+//   s_ray [row]  ray id or -1        s_cnt [row]  k at a ray's first row, 0x80 | j at its j-th row, 0 = padding
+// counters[2] = rows reserved this iteration (a multiple of 128).  keep_flag[ray] is cleared for
+// every live ray here and set by the fused compositor for the rays that stay live.
+__global__ void __launch_bounds__(256) render_march_tiles_kernel(
+    const int* counters_in, int rays_per_call, const int* __restrict__ alive, const int* __restrict__ n_samp,
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, GridView g, const float* __restrict__ t_min,
+    const float* __restrict__ t_max, const uint8_t* __restrict__ hit, float* __restrict__ near, float far_plane,
+    float step_size, float cone_angle, int* __restrict__ s_ray, uint8_t* __restrict__ s_cnt,
+    float* __restrict__ s_ts, float* __restrict__ s_te, uint8_t* __restrict__ keep_flag, int s_cap, int* counters) {
+  const int n_live = counters_in[0];
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n_live + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += blockDim.x * gridDim.x) {
+    float ts[MAX_ITER_SAMPLES], te[MAX_ITER_SAMPLES];
+    int k = 0, ray = -1;
+    if (i < n_live) {
+      ray = alive[i];
+      keep_flag[ray] = 0;
+      const int n = n_samp[ray / rays_per_call];
+      if (n > 0) {
+        const float o[3] = {rays_o[3 * ray], rays_o[3 * ray + 1], rays_o[3 * ray + 2]};
+        const float d[3] = {rays_d[3 * ray], rays_d[3 * ray + 1], rays_d[3 * ray + 2]};
+        const float tsorted[2] = {t_min[ray], t_max[ray]};
+        const uint8_t h = hit[ray];
+        LocalSink sink{ts, te};
+        int n_iv;
+        float t_term;
+        k = march_ray(g, o, d, near[ray], far_plane, &h, tsorted, nullptr, step_size, cone_angle, n, sink, n_iv, t_term);
+        near[ray] = t_term;  // utils.py:1002
+      }
+    }
+    // Rows are reserved with ONE atomicAdd per warp at an arbitrary offset, then the warp's rays are
+    // placed one after the other from that offset, skipping to the next 128-row tile whenever a ray
+    // would straddle a tile boundary.  The reservation covers the worst case of that skipping:
+    // every tile touched can waste at most kmax - 1 rows and therefore holds at least 129 - kmax.
+    const int real = __reduce_add_sync(0xffffffffu, k);
+    const int kmax = __reduce_max_sync(0xffffffffu, k);
+    const int rows = real > 0 ? real + (real / (129 - kmax) + 2) * (kmax - 1) : 0;  // tiles used <= real/(129-kmax)+2
+    int warp_base = 0;
+    if (lane == 0 && rows > 0) {
+      warp_base = atomicAdd(counters + 2, rows);
+      atomicAdd(counters + 6, real);
+    }
+    warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+    if (warp_base + rows > s_cap) {  // capacity exceeded: drop this warp's samples and raise the flag
+      if (lane == 0 && rows > 0) counters[5] = 1;
+      continue;
+    }
+    int pos = 0, run = warp_base & 127;  // `run` is tracked relative to the start of warp_base's tile
+    const int run0 = run;
+    for (int l = 0; l < 32; ++l) {
+      const int kl = __shfl_sync(0xffffffffu, k, l);
+      if ((run & 127) + kl > 128) run = (run + 127) & ~127;
+      if (l == lane) pos = run - run0;
+      run += kl;
+    }
+    // rows after this lane's samples up to the next lane's first row (or the end of the run) are padding
+    int next_pos = __shfl_down_sync(0xffffffffu, pos, 1);
+    if (lane == 31) next_pos = rows;  // the unused tail of the reservation is padding too
+    if (rows > 0) {
+      const int base = warp_base + pos;
+      for (int j = 0; j < k; ++j) {
+        s_ray[base + j] = ray;
+        s_cnt[base + j] = (j == 0) ? (uint8_t)k : (uint8_t)(0x80 | j);  // ray head: #samples; else: offset in ray
+        s_ts[base + j] = ts[j];
+        s_te[base + j] = te[j];
+      }
+      for (int r = pos + k; r < next_pos; ++r) {
+        s_ray[warp_base + r] = -1;
+        s_cnt[warp_base + r] = 0;
+      }
+      if (lane == 0)  // rows skipped before the first ray (it did not fit into the partly used tile)
+        for (int r = 0; r < pos; ++r) {
+          s_ray[warp_base + r] = -1;
+          s_cnt[warp_base + r] = 0;
+        }
+    }
+  }
+}
+
+// Ordered compaction of the live-ray list by keep_flag (single-pass scan with decoupled look-back
+// over chunks taken in ticket order), so the list stays sorted by ray id: neighbouring rays stay
+// neighbours (hash-grid gather locality) and the result does not depend on block scheduling.  Also
+// accumulates the per-call live counts the schedule kernel needs.  `chain` holds one status word per
+// chunk: (generation << 34) | (kind << 32) | value, kind 1 = chunk aggregate, 2 = inclusive prefix;
+// the generation is counters[7], bumped by the schedule kernel, so the array never needs clearing.
+constexpr int CMP_T = 256, CMP_ITEMS = 8, CMP_CHUNK = CMP_T * CMP_ITEMS;
+__global__ void __launch_bounds__(CMP_T) render_compact_kernel(const int* counters_in, int rays_per_call,
+                                                               const int* __restrict__ alive,
+                                                               const uint8_t* __restrict__ keep_flag,
+                                                               int* __restrict__ alive_next, int* __restrict__ n_alive_acc,
+                                                               unsigned long long* chain, int* counters) {
+  __shared__ int s_ticket, s_base, s_warp[CMP_T / 32];
+  const int n_live = counters_in[0];
+  const unsigned long long gen = (unsigned long long)(unsigned int)counters_in[7];
+  const int n_chunks = (n_live + CMP_CHUNK - 1) / CMP_CHUNK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  while (true) {
+    if (threadIdx.x == 0) s_ticket = atomicAdd(counters + 4, 1);
+    __syncthreads();
+    const int ticket = s_ticket;
+    if (ticket >= n_chunks) break;
+    const int first = ticket * CMP_CHUNK + threadIdx.x * CMP_ITEMS;
+    int rays[CMP_ITEMS];
+    unsigned keepmask = 0;
+#pragma unroll
+    for (int j = 0; j < CMP_ITEMS; ++j) {
+      const int idx = first + j;
+      rays[j] = idx < n_live ? alive[idx] : -1;
+      if (rays[j] >= 0 && keep_flag[rays[j]]) keepmask |= 1u << j;
+    }
+    const int cnt = __popc(keepmask);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int warp_off = 0, total = 0;
+    for (int w = 0; w < CMP_T / 32; ++w) {
+      if (w < warp) warp_off += s_warp[w];
+      total += s_warp[w];
+    }
+    if (threadIdx.x == 0) {
+      volatile unsigned long long* vchain = chain;
+      vchain[ticket] = (gen << 34) | (1ull << 32) | (unsigned long long)total;  // publish the aggregate first
+      __threadfence();
+      long long prev = 0;
+      for (int t = ticket - 1; t >= 0; --t) {  // look back until an inclusive prefix is found
+        unsigned long long w;
+        do { w = vchain[t]; } while ((w >> 34) != gen);
+        prev += (long long)(w & 0xffffffffull);
+        if (((w >> 32) & 3ull) == 2ull) break;
+      }
+      vchain[ticket] = (gen << 34) | (2ull << 32) | (unsigned long long)(prev + total);
+      s_base = (int)prev;
+      if (ticket == n_chunks - 1) counters[1] = (int)prev + total;
+    }
+    __syncthreads();
+    int out = s_base + warp_off + inc - cnt;
+#pragma unroll
+    for (int j = 0; j < CMP_ITEMS; ++j)
+      if (keepmask & (1u << j)) alive_next[out++] = rays[j];
+    // per-call live counts (rays of one thread are consecutive list entries: mostly the same call)
+    int cur_call = -1, cur_n = 0;
+#pragma unroll
+    for (int j = 0; j < CMP_ITEMS; ++j)
+      if (keepmask & (1u << j)) {
+        const int c = rays[j] / rays_per_call;
+        if (c != cur_call) {
+          if (cur_n) atomicAdd(n_alive_acc + cur_call, cur_n);
+          cur_call = c, cur_n = 0;
+        }
+        ++cur_n;
+      }
+    if (cur_n) atomicAdd(n_alive_acc + cur_call, cur_n);
+    __syncthreads();
   }
 }
 
@@ -508,6 +679,35 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, counters);
   APNERF_CHECK_LAUNCH("render_march_kernel");
+  return 0;
+}
+
+
+APNERF_API int apnerf_render_march_tiles(int max_live, int rays_per_call, const int* alive, const int* n_samp,
+                                         const float* rays_o, const float* rays_d, int rx, int ry, int rz,
+                                         const uint8_t* binaries, const float* aabbs, const float* t_min,
+                                         const float* t_max, const uint8_t* hit, float* near, float far_plane,
+                                         float step_size, float cone_angle, int* s_ray, uint8_t* s_cnt, float* s_ts,
+                                         float* s_te, uint8_t* keep_flag, int s_cap, int* counters, void* stream) {
+  if (max_live == 0) return 0;
+  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  int mt, mc;
+  apnerf_march_cfg(mt, mc);
+  render_march_tiles_kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
+      counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
+      cone_angle, s_ray, s_cnt, s_ts, s_te, keep_flag, s_cap, counters);
+  APNERF_CHECK_LAUNCH("render_march_tiles_kernel");
+  return 0;
+}
+
+APNERF_API int apnerf_render_compact(int max_live, int rays_per_call, const int* alive, const uint8_t* keep_flag,
+                                     int* alive_next, int* n_alive_acc, void* chain, int* counters, void* stream) {
+  if (max_live == 0) return 0;
+  const int chunks = (max_live + CMP_CHUNK - 1) / CMP_CHUNK;
+  const int cap = apnerf_num_sms() * 4;
+  render_compact_kernel<<<chunks < cap ? chunks : cap, CMP_T, 0, (cudaStream_t)stream>>>(
+      counters, rays_per_call, alive, keep_flag, alive_next, n_alive_acc, (unsigned long long*)chain, counters);
+  APNERF_CHECK_LAUNCH("render_compact_kernel");
   return 0;
 }
 

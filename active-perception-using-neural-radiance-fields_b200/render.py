@@ -5,7 +5,12 @@ Two implementations of the test-mode renderers live here:
 * ``render_image_with_occgrid_test`` / ``render_probablistic_image_with_occgrid_test`` -- the
   drop-ins.  For a single-level occupancy grid (the pipeline's configuration) they run the
   device-driven renderer (csrc/render.cu): the reference's per-call marching schedule is
-  replayed on the GPU with no host synchronisation inside the loop.
+  replayed on the GPU with no host synchronisation inside the loop: per iteration ``schedule ->
+  march -> field (hash grid + MLPs) -> composite``.  ``FusedRenderer.render(fuse_compositor=True)``
+  selects the variant that runs the compositor INSIDE the field kernel's epilogue (tile-aware march,
+  ordered live-list compaction; per-sample network outputs never leave the SM).  Both are tested
+  against each other and the oracle; the stand-alone compositor is the default because it measured
+  ~7 % faster in round 1 (profiles/r01_fused_compositor.md).
 * ``*_unfused`` -- the same algorithm written op by op against the drop-in nerfacc ops, with
   the reference's host-side control flow (``.item()`` per iteration).  Used for multi-level
   grids and as the on-GPU cross-check of the fused path.
@@ -20,7 +25,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
-from ._lib import call, require_cuda
+from ._lib import PreparedCall, call, require_cuda
 from .nerfacc import (
     OccGridEstimator,
     accumulate_along_rays,
@@ -55,7 +60,7 @@ class FusedRenderer:
         self._cap_calls = 0
         self._pinned = None
 
-    def _ensure(self, n_rays, n_calls, s_cap):
+    def _ensure(self, n_rays, n_calls, s_cap, need_rows=False):
         dev = self.device
         if n_rays > self._cap_rays:
             self.t_min = torch.empty(n_rays, device=dev)
@@ -70,23 +75,33 @@ class FusedRenderer:
             self.s_ray = torch.empty(s_cap, device=dev, dtype=torch.int32)
             self.s_ts = torch.empty(s_cap, device=dev)
             self.s_te = torch.empty(s_cap, device=dev)
-            self.rows = torch.empty((s_cap, 40), device=dev, dtype=torch.float16)  # raw fp16 network outputs
             self._cap_samples = s_cap
+        if need_rows and s_cap > getattr(self, "_cap_rows", 0):
+            self.rows = torch.empty((s_cap, 40), device=dev, dtype=torch.float16)  # raw fp16 network outputs
+            self._cap_rows = s_cap
         if n_calls > self._cap_calls:
             self.n_alive_acc = torch.empty(n_calls, device=dev, dtype=torch.int32)
             self.n_samp = torch.empty(n_calls, device=dev, dtype=torch.int32)
             self.iter_samples = torch.empty(n_calls, device=dev, dtype=torch.int32)
             self.total_samples = torch.empty(n_calls, device=dev, dtype=torch.int32)
             self._cap_calls = n_calls
+        if n_rays > getattr(self, "_cap_flags", 0):
+            self.keep_flag = torch.zeros(n_rays, device=dev, dtype=torch.uint8)
+            self.chain = torch.zeros(n_rays // 2048 + 2, device=dev, dtype=torch.int64)
+            self._cap_flags = n_rays
+        if s_cap > getattr(self, "_cap_cnt", 0):
+            self.s_cnt = torch.zeros(s_cap, device=dev, dtype=torch.uint8)
+            self._cap_cnt = s_cap
         if not hasattr(self, "counters"):
-            self.counters = torch.zeros(4, device=dev, dtype=torch.int32)
+            self.counters = torch.zeros(8, device=dev, dtype=torch.int32)
+            self._tag = 0
 
     @torch.no_grad()
     def render(self, radiance_field, estimator: OccGridEstimator, rays_o: Tensor, rays_d: Tensor,
                rays_per_call: int, *, max_samples: int = 1024, near_plane: float = 0.0, far_plane: float = 1e10,
                render_step_size: float = 1e-3, cone_angle: float = 0.0, alpha_thre: float = 0.0,
                early_stop_eps: float = 1e-4, probabilistic: bool = True, state: Optional[Tensor] = None,
-               poll_every: int = 8, debug_hook: Optional[Callable] = None) -> Tensor:
+               poll_every: int = 8, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False) -> Tensor:
         """Render n_rays = n_calls * rays_per_call rays; returns the state [9 + C, n_rays]
         (un-finalised: see ``finalize``).  Nothing is read back to the host except, every
         ``poll_every`` iterations, a non-blocking look at the live-ray counter to stop early."""
@@ -101,8 +116,11 @@ class FusedRenderer:
         assert n_rays % rays_per_call == 0
         n_calls = n_rays // rays_per_call
         min_samples = 1 if cone_angle == 0 else 4
-        s_cap = n_rays * min_samples
-        self._ensure(n_rays, n_calls, s_cap)
+        # rows of the per-iteration sample list: <= min_samples per ray (utils.py:902); the fused layout
+        # pads every warp's run to whole 128-row tiles (<= 2x for the worst non-power-of-two n)
+        # + up to 127 padding rows per 32-ray warp; the kernel refuses (flag) rather than overflow
+        s_cap = n_rays * (min_samples * 2 + 4) + 4096 if fuse_compositor else n_rays * min_samples
+        self._ensure(n_rays, n_calls, s_cap, need_rows=not fuse_compositor)
         if state is None:
             state = torch.empty((self.n_state, n_rays), device=self.device)
         binaries = estimator.binaries.contiguous()
@@ -120,24 +138,54 @@ class FusedRenderer:
             call("apnerf_render_init", n_rays, rays_per_call, rays_o, rays_d, rx, ry, rz, binaries, aabbs,
                  float(near_plane), self.n_state, state, self.t_min, self.t_max, self.hit, self.near, self.alive[1],
                  self.n_alive_acc, self.iter_samples, self.total_samples, n_calls, self.counters)
+            # the per-iteration launch sequence, marshalled once (two variants: the live lists ping-pong)
+            aabb_p = aabb_host.ctypes.data_as(ctypes.c_void_p)
+            meta_p = meta.ctypes.data_as(ctypes.c_void_p)
+            seq = []
+            for parity in range(2):
+                cur, nxt = self.alive[(parity + 1) % 2], self.alive[parity % 2]
+                steps = [PreparedCall("apnerf_render_schedule", n_calls, rays_per_call, int(max_samples), min_samples,
+                                      self.n_alive_acc, self.n_samp, self.iter_samples, self.counters)]
+                if fuse_compositor:
+                    # three launches: tile-aware march -> field + compositor fused -> ordered compaction
+                    steps.append(PreparedCall(
+                        "apnerf_render_march_tiles", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry,
+                        rz, binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
+                        float(render_step_size), float(cone_angle), self.s_ray, self.s_cnt, self.s_ts, self.s_te,
+                        self.keep_flag, int(s_cap), self.counters))
+                    steps.append(PreparedCall(
+                        "apnerf_field_forward_fused", self.counters[2:3], s_cap // 128, self.s_ray, self.s_cnt,
+                        self.s_ts, self.s_te, rays_o, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights,
+                        self.n_sem, state, n_rays, rays_per_call, float(alpha_thre), opc_thre, self.n_samp,
+                        self.iter_samples, int(max_samples), self.keep_flag, self.total_samples,
+                        1 if probabilistic else 0))
+                    steps.append(PreparedCall(
+                        "apnerf_render_compact", n_rays, rays_per_call, cur, self.keep_flag, nxt, self.n_alive_acc,
+                        self.chain, self.counters))
+                else:
+                    steps.append(PreparedCall(
+                        "apnerf_render_march", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry, rz,
+                        binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
+                        float(render_step_size), float(cone_angle), self.entry_base, self.entry_cnt, self.s_ray,
+                        self.s_ts, self.s_te, self.counters))
+                    steps.append(PreparedCall(
+                        "apnerf_field_forward", 0, self.counters[2:3], None, None, self.s_ray, self.s_ts, self.s_te,
+                        rays_o, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights, None, None, 0, 0, None,
+                        0, 0, self.n_sem, None, self.rows, 0, (s_cap + 127) // 128))
+                    steps.append(PreparedCall(
+                        "apnerf_render_composite", n_rays, n_rays, rays_per_call, self.n_sem, cur, self.entry_base,
+                        self.entry_cnt, self.s_ts, self.s_te, self.rows, state, float(alpha_thre), opc_thre,
+                        self.n_samp, self.iter_samples, int(max_samples), nxt, self.n_alive_acc, self.total_samples,
+                        self.counters, 1 if probabilistic else 0))
+                seq.append(steps)
             for it in range(max_iters):
-                cur, nxt = self.alive[(it + 1) % 2], self.alive[it % 2]
-                call("apnerf_render_schedule", n_calls, rays_per_call, int(max_samples), min_samples,
-                     self.n_alive_acc, self.n_samp, self.iter_samples, self.counters)
-                call("apnerf_render_march", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry, rz,
-                     binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
-                     float(render_step_size), float(cone_angle), self.entry_base, self.entry_cnt, self.s_ray,
-                     self.s_ts, self.s_te, self.counters)
+                steps = seq[it % 2]
+                steps[0]()
+                steps[1]()
                 if debug_hook is not None:
                     debug_hook(it, self)
-                call("apnerf_field_forward", 0, self.counters[2:3], None, None, self.s_ray, self.s_ts, self.s_te,
-                     rays_o, rays_d, aabb_host.ctypes.data_as(ctypes.c_void_p), radiance_field.n_levels,
-                     meta.ctypes.data_as(ctypes.c_void_p), table, weights, None, None, 0, 0, None, 0, 0,
-                     self.n_sem, None, self.rows, 0, (s_cap + 127) // 128)
-                call("apnerf_render_composite", n_rays, n_rays, rays_per_call, self.n_sem, cur,
-                     self.entry_base, self.entry_cnt, self.s_ts, self.s_te, self.rows, state,
-                     float(alpha_thre), opc_thre, self.n_samp, self.iter_samples, int(max_samples), nxt,
-                     self.n_alive_acc, self.total_samples, self.counters, 1 if probabilistic else 0)
+                steps[2]()
+                steps[3]()
                 if poll_every and (it + 1) % poll_every == 0:
                     self._pinned[it:it + 1].copy_(self.counters[1:2], non_blocking=True)
                     ev = torch.cuda.Event()
@@ -152,6 +200,12 @@ class FusedRenderer:
                         if int(self._pinned[j]) == 0:
                             return state
         return state
+
+    def check_overflow(self) -> None:
+        """Raise if a marching iteration needed more sample rows than were allocated (host sync)."""
+        if hasattr(self, "counters") and int(self.counters[5].item()) != 0:
+            self.counters[5] = 0
+            raise RuntimeError("apnerf fused renderer: per-iteration sample buffer overflow (results invalid)")
 
     @torch.no_grad()
     def finalize(self, state: Tensor, render_bkgd: Optional[Tensor] = None, want=("rgb", "rgb_var", "opacity", "depth",
@@ -214,6 +268,7 @@ def render_probablistic_image_with_occgrid_test(
                      cone_angle=cone_angle, alpha_thre=alpha_thre, early_stop_eps=early_stop_eps, probabilistic=True)
     o = r.finalize(state, render_bkgd)
     total = int(r.total_samples[0].item())
+    r.check_overflow()
     view = lambda t: t.view((*rays_shape[:-1], -1))
     if C > 0:
         return (view(o["rgb"]), view(o["rgb_var"]), view(o["opacity"]), view(o["depth"]), view(o["depth_var"]),
@@ -243,6 +298,7 @@ def render_image_with_occgrid_test(
                      cone_angle=cone_angle, alpha_thre=alpha_thre, early_stop_eps=early_stop_eps, probabilistic=False)
     o = r.finalize(state, render_bkgd, want=("rgb", "opacity", "depth", "sem"))
     total = int(r.total_samples[0].item())
+    r.check_overflow()
     view = lambda t: t.view((*rays_shape[:-1], -1))
     if C > 0:
         return view(o["rgb"]), view(o["opacity"]), view(o["depth"]), view(o["sem"]), total

@@ -158,7 +158,9 @@ class PredictiveInformationScorer:
             self.partial_sums(c2w, vt, n_traj, sums)
         sums = all_reduce_partial_sums(sums, process_group)
         counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
-        return self.finish(sums.cpu().numpy(), counts)
+        host_sums = sums.cpu().numpy()
+        self.renderer.check_overflow()
+        return self.finish(host_sums, counts)
 
 
 def all_reduce_partial_sums(sums: torch.Tensor, process_group=None) -> torch.Tensor:

@@ -285,24 +285,19 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
 
     peak, peak_kind = _peaks()
     evs, counts = [], []
-    orig = _lib.LIB.call
     r = scorer.renderer
 
-    def timed(name, *a):
-        if name != "apnerf_field_forward":
-            return orig(name, *a)
+    def hook(pc):
+        if pc.name not in ("apnerf_field_forward", "apnerf_field_forward_fused"):
+            return pc.invoke()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        orig(name, *a)
+        pc.invoke()
         a1.record()
         evs.append((a0, a1))
-        counts.append(r.counters[2:3].clone())
+        counts.append(r.counters[6:7].clone() if pc.name.endswith("fused") else r.counters[2:3].clone())
 
-    import apnerf.render as render_mod  # noqa
-    mods = [sys.modules[m] for m in list(sys.modules) if m.endswith(".render") or m.endswith(".scoring")]
-    saved = [(m, m.call) for m in mods if hasattr(m, "call")]
-    for m, _ in saved:
-        m.call = timed
+    _lib.CALL_HOOK = hook
     try:
         sums = torch.zeros((n_traj, 4), device=c2w.device, dtype=torch.float64)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,8 +306,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
         t1.record()
         torch.cuda.synchronize()
     finally:
-        for m, c in saved:
-            m.call = c
+        _lib.CALL_HOOK = None
     k_ms = sum(a.elapsed_time(b) for a, b in evs)
     n_samples = int(torch.cat(counts).sum().item())
     n_launch = sum(1 for c in counts if int(c.item()) > 0)
@@ -320,7 +314,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
     bytes_per_sample = 1024  # 16 levels x 8 corners x 4 features x 2 B
     achieved = n_samples * bytes_per_sample / (k_ms * 1e-3) / 1e9
     n_rays = c2w.shape[0] * scorer.rays_per_view * len(scorer.fields)
-    return {"bound": "hbm", "kernel": "field_forward_kernel (hash-grid gather + fused tcgen05 MLPs)",
+    return {"bound": "hbm", "kernel": "field_forward_kernel (hash-grid gather + fused tcgen05 MLPs + fused compositor)",
             "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " HBM copy GB/s (MEASURED_PEAKS.json)",
             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "algorithmic_bytes_per_sample": bytes_per_sample, "samples_per_step": n_samples,

@@ -143,8 +143,10 @@ int apnerf_sh4(long long n, const float* dirs, void* out, void* stream);
  * (perception/models/utils.py:896-1009) decided entirely on the device.
  * Per-ray state: float [n_state = 9 + n_sem][n_rays] structure-of-arrays
  *   (0-2 rgb, 3 opacity, 4 depth, 5-7 rgb_var, 8 depth_var, 9.. semantic logits).
- * counters: int[4] = {live rays now, live rays collected for the next iteration,
- *                     samples emitted this iteration, iterations that had work}. */
+ * counters: int[8] = {live rays now, live rays collected for the next iteration, samples (rows)
+ *                     emitted this iteration, iterations that had work, compaction ticket,
+ *                     sample-list overflow flag, real samples this iteration, compaction
+ *                     generation}. */
 
 /* Dataset.generate_image_rays (+ the rounded-linspace subsample) --
  * perception/data_proc/habitat_to_data.py:274-301, 461-467.  c2w [n_views,3,4] f32;
@@ -178,6 +180,34 @@ int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_s
                             const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
                             int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
                             void* stream);
+
+/* Fused form of one marching iteration (kernels 1 + 2 + 3 + 4 in three launches): the compositor
+ * of utils.py:937-1009 runs inside the field kernel's epilogue, so per-sample network outputs
+ * never leave the SM.
+ *   apnerf_render_march_tiles : like apnerf_render_march, but every ray's samples are placed inside
+ *       one 128-row tile (s_ray = -1 marks padding rows, s_cnt = #samples at a ray's first row);
+ *       counters[2] = rows reserved (the field kernel clamps it to s_cap); counters[5] is set if
+ *       the s_cap rows did not suffice; keep_flag[ray] cleared for every live ray.
+ *   apnerf_field_forward_fused: hash grid + MLPs + compositing into `state`; sets keep_flag.
+ *   apnerf_render_compact     : ordered compaction of the live list by keep_flag (list stays sorted
+ *       by ray id), per-call live counts; chain: ceil(n_rays/2048)+1 uint64 scratch (never needs
+ *       clearing: entries carry the generation counters[7] that the schedule kernel bumps). */
+int apnerf_render_march_tiles(int max_live, int rays_per_call, const int* alive, const int* n_samp,
+                              const float* rays_o, const float* rays_d, int rx, int ry, int rz,
+                              const uint8_t* binaries, const float* aabbs, const float* t_min,
+                              const float* t_max, const uint8_t* hit, float* near, float far_plane,
+                              float step_size, float cone_angle, int* s_ray, uint8_t* s_cnt, float* s_ts,
+                              float* s_te, uint8_t* keep_flag, int s_cap, int* counters, void* stream);
+int apnerf_field_forward_fused(const int* n_rows_dev, long long max_tiles, const int* s_ray,
+                               const uint8_t* s_cnt, const float* s_ts, const float* s_te,
+                               const float* rays_o, const float* rays_d, const float* aabb_host,
+                               int n_levels, const uint32_t* meta_host, const void* table,
+                               const void* weights, int n_sem, float* state, int n_rays_total,
+                               int rays_per_call, float alpha_thre, float opc_thre, const int* n_samp,
+                               const int* iter_samples, int max_samples, uint8_t* keep_flag,
+                               int* total_samples, int probabilistic, void* stream);
+int apnerf_render_compact(int max_live, int rays_per_call, const int* alive, const uint8_t* keep_flag,
+                          int* alive_next, int* n_alive_acc, void* chain, int* counters, void* stream);
 /* utils.py:1012-1032: background, depth normalisation, [n_rays, D] outputs (any may be NULL). */
 int apnerf_render_finalize(int n_rays, int n_sem, const float* state, float bkgd_r, float bkgd_g,
                            float bkgd_b, float* rgb, float* rgb_var, float* opacity, float* depth,

@@ -65,7 +65,8 @@ def test_generate_rays_matches_reference_formula(apnerf, oracle):
     assert torch.equal(rd2, rd[:w * h][torch.from_numpy(keep).long().to(DEV)])
 
 
-def test_schedule_and_samples_bit_exact(apnerf, oracle):
+@pytest.mark.parametrize("fuse", [False, True])
+def test_schedule_and_samples_bit_exact(apnerf, oracle, fuse):
     """density ~ e^-1 everywhere -> alpha < alpha_thre, opacity stays 0: every implementation
     must take exactly the same marching decisions."""
     field, est = _scene(apnerf, density_gain=0.0)
@@ -81,13 +82,19 @@ def test_schedule_and_samples_bit_exact(apnerf, oracle):
         n = int(r.counters[2].item())
         ray = r.s_ray[:n].cpu().numpy().astype(np.int64)
         ts, te = r.s_ts[:n].cpu().numpy(), r.s_te[:n].cpu().numpy()
+        if fuse:  # tile-aware layout: padding rows carry ray = -1 and no ray straddles a 128-row tile
+            real = ray >= 0
+            cnt = r.s_cnt[:n].cpu().numpy()
+            heads = np.nonzero((cnt > 0) & (cnt < 128))[0]  # k at a ray's first row; 0x80 | j on its other rows
+            assert ((heads % 128) + cnt[heads] <= 128).all(), "a ray's samples must not straddle a tile"
+            ray, ts, te = ray[real], ts[real], te[real]
         order = np.lexsort((ts, ray))
         got.append(dict(n_live=int(r.counters[0].item()), n_samples=int(r.n_samp[0].item()), ray=ray[order],
                         ts=ts[order], te=te[order]))
 
     r = apnerf.FusedRenderer(DEV, 29)
     r.render(field, est, torch.from_numpy(o).to(DEV), torch.from_numpy(d).to(DEV), w * h, max_samples=256,
-             poll_every=0, debug_hook=hook, **OPTS)
+             poll_every=0, debug_hook=hook, fuse_compositor=fuse, **OPTS)
     assert len(trace) >= 10 and sum(len(t["ray_indices"]) for t in trace) > 10000
     for it, t in enumerate(trace):
         g = got[it]
@@ -106,6 +113,13 @@ def test_fused_render_matches_unfused_and_oracle(apnerf, oracle):
     rays = apnerf.Rays(origins=torch.from_numpy(o).to(DEV), viewdirs=torch.from_numpy(d).to(DEV))
     bk = torch.zeros(3, device=DEV)
     fused = apnerf.render_probablistic_image_with_occgrid_test(1024, field, est, rays, render_bkgd=bk, **OPTS)
+    # the variant with the compositor fused into the field kernel's epilogue
+    r4 = apnerf.FusedRenderer(DEV, 29)
+    st4 = r4.render(field, est, rays.origins, rays.viewdirs, w * h, max_samples=1024, fuse_compositor=True, **OPTS)
+    r4.check_overflow()
+    o4 = r4.finalize(st4, bk)
+    for key, a in zip(("rgb", "rgb_var", "opacity", "depth", "depth_var", "sem"), fused[:6]):
+        assert torch.allclose(a, o4[key], rtol=0, atol=1e-6 * max(1.0, float(o4[key].abs().max()))), key
     unfused = apnerf.render.render_probablistic_image_with_occgrid_test_unfused(1024, field, est, rays, render_bkgd=bk,
                                                                                **OPTS)
     orc = oracle.render_probablistic_image_with_occgrid_test(
