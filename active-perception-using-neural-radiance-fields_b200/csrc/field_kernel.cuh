@@ -29,7 +29,7 @@ constexpr int N_EPI_WARPS = 4 * N_CHAINS, N_MMA_WARPS = N_CHAINS, N_ENC_WARPS = 
 constexpr int FIELD_THREADS = (N_EPI_WARPS + N_MMA_WARPS + N_ENC_WARPS) * 32;  // 832
 constexpr int N_ENC_THREADS = N_ENC_WARPS * 32;                                // 512
 constexpr int LEVELS_PER_ENC_THREAD = MAX_LEVELS * TILE_M / N_ENC_THREADS;     // 4
-constexpr int A0_STAGES = 3;
+constexpr int A0_STAGES = 2;
 
 // shared-memory map (bytes).  Per chain ONE 32 KB activation region is reused by every layer:
 //   H  [128 x 128] at +0                      (base layers 1, 2 outputs)
@@ -291,7 +291,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = ptx::smem_u32(smem);
-  // barriers: a0_full[3] | a0_empty[3] | mma_done[2] | epi_done[2] | tmem base slot
+  // barriers: a0_full[A0_STAGES] | a0_empty[A0_STAGES] | mma_done[2] | epi_done[2] | tmem base slot
   const uint32_t bar_full = smem_base + SM_BAR, bar_empty = bar_full + 8 * A0_STAGES,
                  bar_mma = bar_empty + 8 * A0_STAGES, bar_epi = bar_mma + 8 * N_CHAINS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * (2 * A0_STAGES + 2 * N_CHAINS));
