@@ -97,14 +97,25 @@ class FusedRenderer:
             self._tag = 0
 
     @torch.no_grad()
-    def render(self, radiance_field, estimator: OccGridEstimator, rays_o: Tensor, rays_d: Tensor,
+    def render(self, *args, **kwargs) -> Tensor:
+        """Run ``render_iter`` to completion and return the state (see there)."""
+        state = None
+        for state in self.render_iter(*args, **kwargs):
+            pass
+        return state
+
+    @torch.no_grad()
+    def render_iter(self, radiance_field, estimator: OccGridEstimator, rays_o: Tensor, rays_d: Tensor,
                rays_per_call: int, *, max_samples: int = 1024, near_plane: float = 0.0, far_plane: float = 1e10,
                render_step_size: float = 1e-3, cone_angle: float = 0.0, alpha_thre: float = 0.0,
                early_stop_eps: float = 1e-4, probabilistic: bool = True, state: Optional[Tensor] = None,
-               poll_every: int = 8, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False) -> Tensor:
-        """Render n_rays = n_calls * rays_per_call rays; returns the state [9 + C, n_rays]
-        (un-finalised: see ``finalize``).  Nothing is read back to the host except, every
-        ``poll_every`` iterations, a non-blocking look at the live-ray counter to stop early."""
+               poll_every: int = 8, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False):
+        """Render n_rays = n_calls * rays_per_call rays into the state [9 + C, n_rays] (un-finalised: see
+        ``finalize``).  A generator: it enqueues one marching iteration on the CURRENT stream per ``next()``
+        and yields the state tensor, so a caller can interleave several renders on different streams.
+        The device decides everything; the host only (a) stays at most ~2 * poll_every iterations ahead of
+        the GPU and (b) looks at the live-ray counter (pinned memory, copies enqueued every ``poll_every``
+        iterations) to stop enqueuing once every ray has terminated."""
         import ctypes
 
         require_cuda(rays_o, rays_d, estimator.binaries)
@@ -191,15 +202,16 @@ class FusedRenderer:
                     ev = torch.cuda.Event()
                     ev.record()
                     events.append((it, ev))
-                    # look (without waiting) at a copy that has had time to land
-                    while len(events) > 2:
-                        j, e = events[0]
-                        if not e.query():
-                            break
-                        events.pop(0)
-                        if int(self._pinned[j]) == 0:
-                            return state
-        return state
+                    if len(events) > 2:  # throttle: never run more than two polls ahead of the device
+                        events[-3][1].synchronize()
+                    finished = False
+                    while events and events[0][1].query():
+                        j, _ = events.pop(0)
+                        finished = finished or int(self._pinned[j]) == 0
+                    if finished:
+                        break
+                yield state
+        yield state
 
     def check_overflow(self) -> None:
         """Raise if a marching iteration needed more sample rows than were allocated (host sync)."""

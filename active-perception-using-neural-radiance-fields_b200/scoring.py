@@ -71,7 +71,12 @@ class PredictiveInformationScorer:
         else:
             idx = np.round(np.linspace(0, width * height - 1, self.rays_per_view)).astype(np.int32)
             self.keep_idx = torch.from_numpy(idx).to(self.device)
-        self.renderer = FusedRenderer(self.device, self.n_sem)
+        # one renderer (working set) and one stream per ensemble member: the members' marching loops are
+        # independent, so the launch-bound tail iterations of one overlap the wide early iterations of the other
+        self.renderers = [FusedRenderer(self.device, self.n_sem) for _ in self.fields]
+        self.renderer = self.renderers[0]
+        self._streams = None
+        self.interleave = True  # False: render the members one after the other on the current stream
         self._states = None
         self._rays = None
 
@@ -101,11 +106,32 @@ class PredictiveInformationScorer:
                 call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
                      self.rays_per_view, self.keep_idx, rays_o, rays_d)
                 states = []
+                if self._streams is None:
+                    self._streams = [torch.cuda.Stream(device=self.device) for _ in self.fields]
+                main = torch.cuda.current_stream()
+                ready = torch.cuda.Event()
+                ready.record(main)
+                gens = []
                 for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
                     st = self._states[m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
-                    self.renderer.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
-                                         **self.opts)
                     states.append(st)
+                    if not self.interleave:
+                        self.renderers[m].render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
+                                                 **self.opts)
+                        continue
+                    self._streams[m].wait_event(ready)
+                    gens.append(self.renderers[m].render_iter(f, e, rays_o, rays_d, self.rays_per_view,
+                                                              probabilistic=True, state=st, **self.opts))
+                live = list(range(len(gens)))
+                while live:  # enqueue the members' marching iterations alternately, each on its own stream
+                    for m in list(live):
+                        with torch.cuda.stream(self._streams[m]):
+                            if next(gens[m], None) is None:
+                                live.remove(m)
+                for m in range(len(gens)):
+                    done = torch.cuda.Event()
+                    done.record(self._streams[m])
+                    main.wait_event(done)
                 states += [None] * (4 - len(states))
                 call("apnerf_score_views", len(self.fields), states[0], states[1], states[2], states[3], nr,
                      self.rays_per_view, self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
@@ -159,7 +185,8 @@ class PredictiveInformationScorer:
         sums = all_reduce_partial_sums(sums, process_group)
         counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
         host_sums = sums.cpu().numpy()
-        self.renderer.check_overflow()
+        for r in self.renderers:
+            r.check_overflow()
         return self.finish(host_sums, counts)
 
 

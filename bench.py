@@ -295,9 +295,14 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
         pc.invoke()
         a1.record()
         evs.append((a0, a1))
-        counts.append(r.counters[6:7].clone() if pc.name.endswith("fused") else r.counters[2:3].clone())
+        cnt = pc.keep[0].new_empty(0)  # locate the renderer this call belongs to through its counters tensor
+        for rr in scorer.renderers:
+            if any(t.data_ptr() == rr.counters[2:3].data_ptr() for t in pc.keep):
+                cnt = rr.counters[6:7].clone() if pc.name.endswith("fused") else rr.counters[2:3].clone()
+        counts.append(cnt)
 
     _lib.CALL_HOOK = hook
+    scorer.interleave = False  # time the members' kernels without cross-stream contention
     try:
         sums = torch.zeros((n_traj, 4), device=c2w.device, dtype=torch.float64)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -307,6 +312,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
         torch.cuda.synchronize()
     finally:
         _lib.CALL_HOOK = None
+        scorer.interleave = True
     k_ms = sum(a.elapsed_time(b) for a, b in evs)
     n_samples = int(torch.cat(counts).sum().item())
     n_launch = sum(1 for c in counts if int(c.item()) > 0)
