@@ -54,7 +54,7 @@ class PredictiveInformationScorer:
     def __init__(self, radiance_fields: Sequence[torch.nn.Module], estimators: Sequence[torch.nn.Module], width: int,
                  height: int, focal: float, *, near_plane: float = 0.1, render_step_size: float = 1e-3,
                  cone_angle: float = 0.004, alpha_thre: float = 0.01, scale: float = 1.0, max_samples: int = 1024,
-                 device="cuda:0", views_per_batch: int = 32):
+                 device="cuda:0", views_per_batch: int = 32, concurrent_batches: int = 1):
         assert 1 <= len(radiance_fields) <= 4 and len(radiance_fields) == len(estimators)
         self.fields, self.estimators = list(radiance_fields), list(estimators)
         self.width, self.height, self.focal = int(width), int(height), float(focal)
@@ -71,20 +71,28 @@ class PredictiveInformationScorer:
         else:
             idx = np.round(np.linspace(0, width * height - 1, self.rays_per_view)).astype(np.int32)
             self.keep_idx = torch.from_numpy(idx).to(self.device)
-        # one renderer (working set) and one stream per ensemble member: the members' marching loops are
-        # independent, so the launch-bound tail iterations of one overlap the wide early iterations of the other
-        self.renderers = [FusedRenderer(self.device, self.n_sem) for _ in self.fields]
-        self.renderer = self.renderers[0]
+        # Renders in flight: `concurrent_batches` view batches x the ensemble members, each with its own
+        # working set and stream.  The marching loops are independent, so the narrow, launch-bound tail
+        # iterations of one render overlap the wide early iterations of the others.
+        self.concurrent_batches = max(1, int(concurrent_batches))
+        self.renderers = [[FusedRenderer(self.device, self.n_sem) for _ in self.fields]
+                          for _ in range(self.concurrent_batches)]
+        self.renderer = self.renderers[0][0]
         self._streams = None
-        self.interleave = True  # False: render the members one after the other on the current stream
+        self.interleave = True  # False: one render after the other on the current stream (measurement)
         self._states = None
         self._rays = None
 
+    def all_renderers(self):
+        return [r for slot in self.renderers for r in slot]
+
     def _buffers(self, n_views):
         n_rays = n_views * self.rays_per_view
-        if self._rays is None or self._rays[0].shape[0] < n_rays:
-            self._rays = (torch.empty((n_rays, 3), device=self.device), torch.empty((n_rays, 3), device=self.device))
-            self._states = [torch.empty((9 + self.n_sem, n_rays), device=self.device) for _ in self.fields]
+        if self._rays is None or self._rays[0][0].shape[0] < n_rays:
+            self._rays = [(torch.empty((n_rays, 3), device=self.device), torch.empty((n_rays, 3), device=self.device))
+                          for _ in range(self.concurrent_batches)]
+            self._states = [[torch.empty((9 + self.n_sem, n_rays), device=self.device) for _ in self.fields]
+                            for _ in range(self.concurrent_batches)]
         return n_rays
 
     @torch.no_grad()
@@ -92,49 +100,56 @@ class PredictiveInformationScorer:
                      sums: Optional[torch.Tensor] = None) -> torch.Tensor:
         """c2w [n_views, 3, 4] f32 and view_traj [n_views] i32 ON THE DEVICE -> float64 [n_traj, 4]
         sums of the per-pixel (rgb, depth, sem, occ) predictive-information terms.  Everything is
-        enqueued on the current stream; nothing is read back."""
+        enqueued on CUDA streams; nothing is read back except the renderers' non-blocking look at
+        their live-ray counters."""
         n_views = c2w.shape[0]
         if sums is None:
             sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
         vb = self.views_per_batch
         self._buffers(min(vb, n_views))
+        E, K = len(self.fields), self.concurrent_batches
         with torch.cuda.device(self.device):
-            for v0 in range(0, n_views, vb):
-                v1 = min(n_views, v0 + vb)
-                nr = (v1 - v0) * self.rays_per_view
-                rays_o, rays_d = self._rays[0][:nr], self._rays[1][:nr]
-                call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
-                     self.rays_per_view, self.keep_idx, rays_o, rays_d)
-                states = []
-                if self._streams is None:
-                    self._streams = [torch.cuda.Stream(device=self.device) for _ in self.fields]
-                main = torch.cuda.current_stream()
-                ready = torch.cuda.Event()
-                ready.record(main)
-                gens = []
-                for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
-                    st = self._states[m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
-                    states.append(st)
-                    if not self.interleave:
-                        self.renderers[m].render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
-                                                 **self.opts)
-                        continue
-                    self._streams[m].wait_event(ready)
-                    gens.append(self.renderers[m].render_iter(f, e, rays_o, rays_d, self.rays_per_view,
-                                                              probabilistic=True, state=st, **self.opts))
+            if self._streams is None:
+                self._streams = [[torch.cuda.Stream(device=self.device) for _ in range(E)] for _ in range(K)]
+            main = torch.cuda.current_stream()
+            batches = [(v0, min(n_views, v0 + vb)) for v0 in range(0, n_views, vb)]
+            for g0 in range(0, len(batches), K):
+                group = batches[g0:g0 + K]
+                gens, work = [], []
+                for slot, (v0, v1) in enumerate(group):
+                    nr = (v1 - v0) * self.rays_per_view
+                    rays_o, rays_d = self._rays[slot][0][:nr], self._rays[slot][1][:nr]
+                    call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
+                         self.rays_per_view, self.keep_idx, rays_o, rays_d)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    states = []
+                    for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
+                        st = self._states[slot][m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
+                        states.append(st)
+                        r = self.renderers[slot][m]
+                        if not self.interleave:
+                            r.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st, **self.opts)
+                            continue
+                        self._streams[slot][m].wait_event(ready)
+                        gens.append((self._streams[slot][m],
+                                     r.render_iter(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True,
+                                                   state=st, **self.opts)))
+                    work.append((v0, v1, nr, states))
                 live = list(range(len(gens)))
-                while live:  # enqueue the members' marching iterations alternately, each on its own stream
-                    for m in list(live):
-                        with torch.cuda.stream(self._streams[m]):
-                            if next(gens[m], None) is None:
-                                live.remove(m)
-                for m in range(len(gens)):
+                while live:  # enqueue the renders' marching iterations round-robin, each on its own stream
+                    for i in list(live):
+                        with torch.cuda.stream(gens[i][0]):
+                            if next(gens[i][1], None) is None:
+                                live.remove(i)
+                for stream, _ in gens:
                     done = torch.cuda.Event()
-                    done.record(self._streams[m])
+                    done.record(stream)
                     main.wait_event(done)
-                states += [None] * (4 - len(states))
-                call("apnerf_score_views", len(self.fields), states[0], states[1], states[2], states[3], nr,
-                     self.rays_per_view, self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
+                for v0, v1, nr, states in work:
+                    states = states + [None] * (4 - len(states))
+                    call("apnerf_score_views", E, states[0], states[1], states[2], states[3], nr, self.rays_per_view,
+                         self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
         return sums
 
     @staticmethod
@@ -185,7 +200,7 @@ class PredictiveInformationScorer:
         sums = all_reduce_partial_sums(sums, process_group)
         counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
         host_sums = sums.cpu().numpy()
-        for r in self.renderers:
+        for r in self.all_renderers():
             r.check_overflow()
         return self.finish(host_sums, counts)
 

@@ -192,7 +192,8 @@ def run_ours(args):
         f = apnerf.NGPRadianceField(synthetic.ROI_AABB, layers=2, num_semantic_classes=N_SEM)
         fields.append(synthetic.init_trained_like(f, seed=s).to(dev).eval())
     scorer = apnerf.PredictiveInformationScorer(fields, [est, est], W, H, HFOV_FOCAL, device=dev,
-                                                views_per_batch=V, **OPTS)
+                                                views_per_batch=max(1, V // args.concurrent_batches),
+                                                concurrent_batches=args.concurrent_batches, **OPTS)
     n_traj = max(1, (V * world) // 32)
     poses_all = synthetic.make_poses(V * world, seed=3)
     view_traj_all = (np.arange(V * world) // 32).astype(np.int32) if V * world >= 32 else np.zeros(V * world, np.int32)
@@ -296,7 +297,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
         a1.record()
         evs.append((a0, a1))
         cnt = pc.keep[0].new_empty(0)  # locate the renderer this call belongs to through its counters tensor
-        for rr in scorer.renderers:
+        for rr in scorer.all_renderers():
             if any(t.data_ptr() == rr.counters[2:3].data_ptr() for t in pc.keep):
                 cnt = rr.counters[6:7].clone() if pc.name.endswith("fused") else rr.counters[2:3].clone()
         counts.append(cnt)
@@ -320,6 +321,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
     bytes_per_sample = 1024  # 16 levels x 8 corners x 4 features x 2 B
     achieved = n_samples * bytes_per_sample / (k_ms * 1e-3) / 1e9
     n_rays = c2w.shape[0] * scorer.rays_per_view * len(scorer.fields)
+    r = None
     return {"bound": "hbm", "kernel": "field_forward_kernel (hash-grid gather + fused tcgen05 MLPs + fused compositor)",
             "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " HBM copy GB/s (MEASURED_PEAKS.json)",
             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -337,6 +339,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--views-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--concurrent-batches", type=int, default=1,
+                    help="view batches rendered concurrently per GPU (each x the ensemble members, own streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
