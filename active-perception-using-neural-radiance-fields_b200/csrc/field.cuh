@@ -115,44 +115,6 @@ __device__ __forceinline__ uint2 blend_level(const float w[3], const uint2 v[8])
   return o;
 }
 
-// Four consecutive levels at once: all 32 gathers are issued before the first blend so the
-// memory system sees them together (a level-at-a-time loop leaves the gather latency-bound:
-// ncu showed the L1 data pipe at 41 % with the encoder warps parked on long-scoreboard stalls).
-// Same arithmetic as encode_level, level by level.
-__device__ __forceinline__ void encode_level_quad(const HashGridMeta& m, int l, const float x[3],
-                                                  const uint2* __restrict__ table, uint2 out[4]) {
-  uint32_t cell[4][3];
-  float w[4][3];
-  uint2 v[4][8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int li = (l + i) < m.n_levels ? (l + i) : 0;
-    level_cell(m, li, x, cell[i], w[i]);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[i][c] = __ldg(table + corner_index(m, li, cell[i], c));
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) out[i] = ((l + i) < m.n_levels) ? blend_level(w[i], v[i]) : make_uint2(0u, 0u);
-}
-
-// Two consecutive levels at once (16 gathers in flight): the variant used when the register
-// budget is 96 per thread (18 resident warps).
-__device__ __forceinline__ void encode_level_pair(const HashGridMeta& m, int l, const float x[3],
-                                                  const uint2* __restrict__ table, uint2& out0, uint2& out1) {
-  uint32_t cell0[3], cell1[3];
-  float w0[3], w1[3];
-  const bool has0 = l < m.n_levels, has1 = (l + 1) < m.n_levels;
-  level_cell(m, has0 ? l : 0, x, cell0, w0);
-  level_cell(m, has1 ? l + 1 : 0, x, cell1, w1);
-  uint2 v0[8], v1[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) v0[c] = __ldg(table + corner_index(m, has0 ? l : 0, cell0, c));
-#pragma unroll
-  for (int c = 0; c < 8; ++c) v1[c] = __ldg(table + corner_index(m, has1 ? l + 1 : 0, cell1, c));
-  out0 = has0 ? blend_level(w0, v0) : make_uint2(0u, 0u);
-  out1 = has1 ? blend_level(w1, v1) : make_uint2(0u, 0u);
-}
-
 // Real spherical harmonics, degree 4 (16 coefficients), evaluated on d itself: the reference
 // feeds (d + 1) / 2 (ngp.py:205) and tcnn maps it back with 2u - 1.  Every product / sum is
 // individually rounded (the file is compiled with --fmad=false).
