@@ -348,8 +348,9 @@ __global__ void __launch_bounds__(CMP_T) render_compact_kernel(const int* counte
 // semantic logits, then the variance terms against the UPDATED running rgb / depth
 // (utils.py:957-999), next ray mask (utils.py:1004-1009) and compaction of the live list.
 // (A 4-lanes-per-ray variant was measured slower: the weights' exp() calls were then issued by every
-// lane and the kernel became MUFU-bound.)  The per-sample weight / colour / midpoint of the first
-// pass are kept in registers for the common case k <= 4 so the variance pass costs no exp().
+// lane and the kernel became MUFU-bound.)  The weights of the first pass are kept in a small per-thread
+// array and the 32 semantic accumulators are processed 16 at a time, which keeps the kernel at ~80
+// registers (6 CTAs of 128 threads per SM instead of 3): it is latency-bound on the scattered per-ray state.
 // Sample row (40 fp16): [density logit, r, g, b logits, sigma as fp32 (2 halves), 0, 0 | 32 sem logits].
 struct SampleTerms {
   float w, col[3], tmid;
@@ -373,7 +374,7 @@ __device__ __forceinline__ SampleTerms sample_terms(const uint4& r0, float t0, f
 }
 
 template <bool PROB>
-__global__ void __launch_bounds__(128) render_composite_kernel(
+__global__ void __launch_bounds__(128, 6) render_composite_kernel(
     const int* counters_in, int n_rays, int rays_per_call, int n_sem,
     const int* __restrict__ alive, const int* __restrict__ entry_base, const int* __restrict__ entry_cnt,
     const float* __restrict__ s_ts, const float* __restrict__ s_te, const uint4* __restrict__ rows,
@@ -395,13 +396,12 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
       float* st = state + ray;
       float opac = st[ST_OPA * NR];
       if (k > 0) {
+        // pass 1: weights (kept in a small per-thread array: registers stay low, occupancy high),
+        // rgb / opacity / depth
+        float wloc[MAX_ITER_SAMPLES];  // weight of sample j, or -1 when filtered by alpha_thre
         const float prefix = __fsub_rn(1.0f, opac);
         float rgb[3] = {st[0], st[NR], st[2 * NR]};
         float depth = st[ST_DEPTH * NR];
-        float sem[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) sem[c] = (c < n_sem) ? st[(ST_SEM + c) * NR] : 0.f;
-        SampleTerms cache[4];
         float esum = 0.f;
         for (int j = 0; j < k; ++j) {
           const int s = base + j;
@@ -409,53 +409,31 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
           float sdt;
           const SampleTerms tm = sample_terms(r0, s_ts[s], s_te[s], esum, prefix, alpha_thre, sdt);
           esum = __fadd_rn(esum, sdt);
-          if (PROB) {  // static indices only: stays in registers
-            if (j == 0) cache[0] = tm;
-            else if (j == 1) cache[1] = tm;
-            else if (j == 2) cache[2] = tm;
-            else if (j == 3) cache[3] = tm;
-          }
+          wloc[j] = tm.vis ? tm.w : -1.0f;
           if (!tm.vis) continue;
           ++n_vis;
 #pragma unroll
           for (int c = 0; c < 3; ++c) rgb[c] = __fadd_rn(rgb[c], __fmul_rn(tm.w, tm.col[c]));
           opac = __fadd_rn(opac, tm.w);
           depth = __fadd_rn(depth, __fmul_rn(tm.w, tm.tmid));
-          __align__(16) __half h[32];
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) reinterpret_cast<uint4*>(h)[qd] = __ldg(rows + (size_t)s * 5 + 1 + qd);
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < n_sem) sem[c] = __fadd_rn(sem[c], __fmul_rn(tm.w, __half2float(h[c])));
         }
-        if (PROB) {
+        if (PROB) {  // variance terms against the UPDATED running rgb / depth
           float rv[3] = {st[ST_RGBVAR * NR], st[(ST_RGBVAR + 1) * NR], st[(ST_RGBVAR + 2) * NR]};
           float dv = st[ST_DVAR * NR];
-          auto add_var = [&](const SampleTerms& tm) {
-            if (!tm.vis) return;
+          for (int j = 0; j < k; ++j) {
+            const float w = wloc[j];
+            if (w < 0.f) continue;
+            const int s = base + j;
+            const uint4 r0 = __ldg(rows + (size_t)s * 5);
+            const __half* h0 = reinterpret_cast<const __half*>(&r0);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float df = __fsub_rn(tm.col[c], rgb[c]);
-              rv[c] = __fadd_rn(rv[c], __fmul_rn(tm.w, __fmul_rn(df, df)));
+              const float col = 1.0f / (1.0f + expf(-__half2float(h0[1 + c])));
+              const float df = __fsub_rn(col, rgb[c]);
+              rv[c] = __fadd_rn(rv[c], __fmul_rn(w, __fmul_rn(df, df)));
             }
-            const float dd = __fsub_rn(tm.tmid, depth);
-            dv = __fadd_rn(dv, __fmul_rn(tm.w, __fmul_rn(dd, dd)));
-          };
-          if (k <= 4) {
-            add_var(cache[0]);
-            if (k > 1) add_var(cache[1]);
-            if (k > 2) add_var(cache[2]);
-            if (k > 3) add_var(cache[3]);
-          } else {
-            esum = 0.f;
-            for (int j = 0; j < k; ++j) {
-              const int s = base + j;
-              const uint4 r0 = __ldg(rows + (size_t)s * 5);
-              float sdt;
-              const SampleTerms tm = sample_terms(r0, s_ts[s], s_te[s], esum, prefix, alpha_thre, sdt);
-              esum = __fadd_rn(esum, sdt);
-              add_var(tm);
-            }
+            const float dd = __fsub_rn(__fmul_rn(__fadd_rn(s_ts[s], s_te[s]), 0.5f), depth);
+            dv = __fadd_rn(dv, __fmul_rn(w, __fmul_rn(dd, dd)));
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) st[(ST_RGBVAR + c) * NR] = rv[c];
@@ -465,9 +443,26 @@ __global__ void __launch_bounds__(128) render_composite_kernel(
         for (int c = 0; c < 3; ++c) st[c * NR] = rgb[c];
         st[ST_OPA * NR] = opac;
         st[ST_DEPTH * NR] = depth;
+        // pass 2: semantic logits, 16 channels (two 16-byte chunks of the row) at a time
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          if (16 * g >= n_sem) break;
+          float acc[16];
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < n_sem) st[(ST_SEM + c) * NR] = sem[c];
+          for (int c = 0; c < 16; ++c) acc[c] = (16 * g + c < n_sem) ? st[(ST_SEM + 16 * g + c) * NR] : 0.f;
+          for (int j = 0; j < k; ++j) {
+            const float w = wloc[j];
+            if (w < 0.f) continue;
+            __align__(16) __half h[16];
+            reinterpret_cast<uint4*>(h)[0] = __ldg(rows + (size_t)(base + j) * 5 + 1 + 2 * g);
+            reinterpret_cast<uint4*>(h)[1] = __ldg(rows + (size_t)(base + j) * 5 + 2 + 2 * g);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w, __half2float(h[c])));
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (16 * g + c < n_sem) st[(ST_SEM + 16 * g + c) * NR] = acc[c];
+        }
       }
       const int n = n_samp[call];
       keep = (n > 0) && (opac <= opc_thre) && (k == n) && (iter_samples[call] < max_samples);
