@@ -174,7 +174,9 @@ class PredictiveInformationScorer:
         poses, owner = [], []
         for t, traj in enumerate(trajectories):
             traj = np.asarray(traj)
-            idx = uncertainty_view_indices(len(traj)) if len(traj) >= 40 else np.arange(len(traj))
+            # always the reference's 40 indices: a short trajectory repeats views (and, below 20 poses, numpy's
+            # negative indices wrap) exactly as trajectory[unc_idx] does at pipeline.py:687-697
+            idx = uncertainty_view_indices(len(traj))
             poses.append(traj[idx])
             owner += [t] * len(idx)
         poses = np.concatenate(poses, 0)

@@ -19,8 +19,11 @@ Parity status
 * hash-grid / SH / MLP (tiny-cuda-nn): **parity unpinned** -- external unpinned dependency,
   absent from /root/reference (perception/models/requirements.txt:1); restated from its
   published algorithm.
-* scoring (scripts/pipeline.py:727-781): restated; pipeline.py cannot be imported here
-  (habitat_sim, lpips), so **parity unpinned** beyond a line-by-line restatement.
+* test-mode renderer (utils.py:782-1032), ray generation / subsample (habitat_to_data.py:274-301,
+  462-467) and scoring (scripts/pipeline.py:666-798): PINNED against the reference's own Python,
+  imported unmodified from /root/reference and run on CPU by tests/golden/make_golden.py (native
+  calls served by apnerf_oracle.c, field by the restatement below); fixtures in
+  tests/golden/reference_python_path.npz, checked by tests/test_golden.py.
 """
 from __future__ import annotations
 
