@@ -11,6 +11,7 @@ from .radiance_fields import NGPRadianceField  # noqa: F401
 from .render import (  # noqa: F401
     FusedRenderer,
     Rays,
+    render_image_with_occgrid,
     render_image_with_occgrid_test,
     render_image_with_occgrid_with_depth_guide,
     render_probablistic_image_with_occgrid_test,
@@ -19,5 +20,5 @@ from .render import (  # noqa: F401
 from .scoring import PredictiveInformationScorer, probablistic_uncertainty  # noqa: F401
 
 __all__ = ["nerfacc", "radiance_fields", "render", "scoring", "synthetic", "OccGridEstimator", "NGPRadianceField",
-           "FusedRenderer", "Rays", "render_image_with_occgrid_test", "render_probablistic_image_with_occgrid_test",
+           "FusedRenderer", "Rays", "render_image_with_occgrid", "render_image_with_occgrid_test", "render_probablistic_image_with_occgrid_test",
            "render_image_with_occgrid_with_depth_guide", "sem_rendering", "training", "PredictiveInformationScorer", "probablistic_uncertainty", "_lib"]

@@ -452,6 +452,19 @@ def sem_rendering(
     return colors, opacities, depths, semantics, extras
 
 
+def render_image_with_occgrid(
+    radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays, near_plane: float = 0.0,
+    far_plane: float = 1e10, render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,
+    cone_angle: float = 0.0, alpha_thre: float = 0.0, test_chunk_size: int = 8192,
+    timestamps: Optional[torch.Tensor] = None,
+):
+    """Drop-in for perception/models/utils.py:222-359 (the depth-guided variant below without the guide)."""
+    return render_image_with_occgrid_with_depth_guide(
+        radiance_field, estimator, rays, near_plane=near_plane, far_plane=far_plane, render_step_size=render_step_size,
+        render_bkgd=render_bkgd, cone_angle=cone_angle, alpha_thre=alpha_thre, test_chunk_size=test_chunk_size,
+        timestamps=timestamps, depth=None)
+
+
 def render_image_with_occgrid_with_depth_guide(
     radiance_field: torch.nn.Module, estimator: OccGridEstimator, rays: Rays, near_plane: float = 0.0,
     far_plane: float = 1e10, render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,

@@ -153,12 +153,16 @@ class OracleField(torch.nn.Module):
         synthetic.init_trained_like(f, seed=seed, density_gain=density_gain)
         self.num_semantic_classes = n_classes
         self._fp = O.FieldParams(f.mlp_base.params.detach().numpy(), f.mlp_head.params.detach().numpy(),
-                                 f.mlp_sem.params.detach().numpy(), num_semantic_classes=n_classes)
+                                 f.mlp_sem.params.detach().numpy() if n_classes > 0 else None,
+                                 num_semantic_classes=n_classes)
         self._aabb = f.aabb.numpy()
 
     def forward(self, positions, directions):
-        rgb, sigma, sem = O.field_forward(positions.numpy(), directions.numpy(), self._aabb, self._fp)
-        return _t(rgb), _t(sigma).reshape(-1, 1), _t(sem)
+        out = O.field_forward(positions.numpy(), directions.numpy(), self._aabb, self._fp)
+        return (_t(out[0]), _t(out[1]).reshape(-1, 1)) + tuple(_t(o) for o in out[2:])
+
+    def query_density(self, positions):
+        return _t(O.field_forward(positions.numpy(), None, self._aabb, self._fp, density_only=True)).reshape(-1, 1)
 
 
 def build_scene(OccGridEstimator):
@@ -235,5 +239,92 @@ def main():
     print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
 
 
+def main_sampling():
+    """Second fixture: the op boundary (OccGridEstimator.sampling, rendering, _update) and the remaining
+    render wrappers of utils.py, all from the reference's Python in eval mode (stratified=False)."""
+    sys.path.insert(0, HERE)
+    import patterns as P
+    utils, Dataset, OccGridEstimator = import_reference()
+    from apnerf import synthetic
+    from datasets.utils import Rays
+    from nerfacc.volrend import rendering
+    out = {}
+    traj = synthetic.make_poses(4, seed=CFG["pose_seed"])
+    w, h = 32, 24
+    pose = torch.from_numpy(synthetic.pose_to_matrix(traj[1])).unsqueeze(0).float()
+    K = np.array([[w / 2.0, 0, w / 2], [0, w / 2.0, h / 2], [0, 0, 1.0]])
+    rs = Dataset.generate_image_rays(pose, w, h, K, "cpu")
+    out["rays_o"], out["rays_d"] = rs.origins.numpy(), rs.viewdirs.numpy()
+
+    def estimator(levels, seed):
+        est = OccGridEstimator(torch.tensor(synthetic.ROI_AABB), resolution=CFG["grid_res"], levels=levels)
+        b = synthetic.make_occupancy(CFG["grid_res"], seed=seed)
+        if levels > 1:  # outer levels: the same pattern, sparser
+            b = torch.cat([b] + [synthetic.make_occupancy(CFG["grid_res"], n_boxes=12, seed=seed + l) for l in range(1, levels)])
+        est.binaries = b
+        est.occs = b.flatten().float()
+        return est.eval()
+
+    # ---- S1: sampling with a density pre-filter (1 level) and plain traversal (2 levels)
+    e1, e2 = estimator(1, 1), estimator(2, 4)
+    ri, ts, te = e1.sampling(rs.origins, rs.viewdirs, sigma_fn=P.sigma_pattern, near_plane=0.1, far_plane=1e10,
+                             render_step_size=5e-3, stratified=False, cone_angle=0.004, alpha_thre=0.01)
+    out["s1_ray_indices"], out["s1_t_starts"], out["s1_t_ends"] = ri.numpy(), ts.numpy(), te.numpy()
+    ri2, ts2, te2 = e2.sampling(rs.origins, rs.viewdirs, near_plane=0.2, far_plane=30.0, render_step_size=2e-2,
+                                stratified=False, cone_angle=0.0, alpha_thre=0.0, early_stop_eps=0.0)
+    out["s2_ray_indices"], out["s2_t_starts"], out["s2_t_ends"] = ri2.numpy(), ts2.numpy(), te2.numpy()
+    print("sampling:", len(ri), "samples after the visibility filter;", len(ri2), "plain on 2 levels")
+
+    # ---- S2: nerfacc.rendering on S1's samples
+    bk = torch.tensor([0.1, 0.2, 0.3])
+    rgb, opa, dep, extras = rendering(ts, te, torch.as_tensor(ri), n_rays=w * h, rgb_sigma_fn=P.rgb_sigma_pattern,
+                                      render_bkgd=bk)
+    out["r_rgb"], out["r_opacity"], out["r_depth"] = rgb.numpy(), opa.numpy(), dep.numpy()
+    out["r_weights"] = extras["weights"].numpy()
+
+    # ---- S3: the render wrappers of utils.py, eval mode, oracle field
+    field = OracleField(__import__("apnerf"), CFG["field_seeds"][0], CFG["n_classes"], CFG["density_gain"]).eval()
+    plain = OracleField(__import__("apnerf"), CFG["field_seeds"][1], 0, CFG["density_gain"]).eval()
+    rays = Rays(origins=rs.origins, viewdirs=rs.viewdirs)
+    opts = dict(near_plane=CFG["near_plane"], render_step_size=4e-3, cone_angle=CFG["cone_angle"],
+                alpha_thre=CFG["alpha_thre"], render_bkgd=bk)
+    with torch.no_grad():
+        g = utils.render_image_with_occgrid_with_depth_guide(field, e1, rays, depth=torch.full((w * h,), 2.0), **opts)
+        for name, v in zip(("rgb", "opacity", "depth", "sem"), g[:4]):
+            out[f"guide_{name}"] = v.numpy()
+        out["guide_n"] = np.int64(g[4])
+        g = utils.render_image_with_occgrid(plain, e1, rays, test_chunk_size=300, **opts)
+        for name, v in zip(("rgb", "opacity", "depth"), g[:3]):
+            out[f"occgrid_{name}"] = v.numpy()
+        out["occgrid_n"] = np.int64(g[3])
+        g = utils.render_image_with_occgrid_test(1024, plain, e1, rays, **opts)
+        for name, v in zip(("rgb", "opacity", "depth"), g[:3]):
+            out[f"test_{name}"] = v.numpy()
+        out["test_n"] = np.int64(g[3])
+    print("wrappers: samples", int(out["guide_n"]), int(out["occgrid_n"]), int(out["test_n"]))
+
+    # ---- S4: OccGridEstimator._update, warm-up branch (all cells), jitter patched to the cell centre
+    res = 32
+    eu = OccGridEstimator(torch.tensor(synthetic.ROI_AABB), resolution=res, levels=2)
+    eu.occs[::7] = 0.03
+    eu.occs[5::11] = -1.0  # cells no camera sees (mark_invisible_cells) are skipped
+    real_rand_like = torch.rand_like
+    torch.rand_like = P.half_like
+    try:
+        for step in (0, 16):
+            eu._update(step=step, occ_eval_fn=P.occ_pattern(eu.aabbs[0], res), occ_thre=0.01, ema_decay=0.95)
+    finally:
+        torch.rand_like = real_rand_like
+    out["upd_occs"], out["upd_binaries"] = eu.occs.numpy(), eu.binaries.numpy()
+    print("update: occupied", int(eu.binaries.sum()), "of", eu.binaries.numel())
+
+    dst = os.path.join(HERE, "reference_python_ops.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--ops" in sys.argv:
+        main_sampling()
+    else:
+        main()
