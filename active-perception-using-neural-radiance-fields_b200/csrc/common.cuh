@@ -73,7 +73,7 @@ static inline void apnerf_march_cfg(int& threads, int& ctas_per_sm) {
   static int t = 0, c = 0;
   if (t == 0) {
     const char* e = getenv("APNERF_MARCH_CFG");
-    if (!e || sscanf(e, "%d,%d", &t, &c) != 2) t = 256, c = 4;
+    if (!e || sscanf(e, "%d,%d", &t, &c) != 2) t = 256, c = 5;
   }
   threads = t, ctas_per_sm = c;
 }

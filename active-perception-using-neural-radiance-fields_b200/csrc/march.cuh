@@ -160,12 +160,17 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
       delta[a] = (d[a] == 0.0f) ? this_tmax : __fmul_rn(__fmul_rn(voxel, inv[a]), sf);
       ovf[a] = fin + stp[a];
     }
-    const int64_t level_base = (int64_t)level * g.rx * g.ry * g.rz;
+    // The cell id is kept incrementally (cur[] itself is only needed for the start cell) and the
+    // "stepped onto the overflow cell" test cur[a] == ovf[a] (utils_grid.cuh:131-141) as a per-axis
+    // difference that a step reduces by stp[a]: the same predicate, fewer instructions per cell.
+    const uint8_t* __restrict__ lvl_bin = g.binaries + (int64_t)level * g.rx * g.ry * g.rz;
+    int cid = cur[0] * g.ry * g.rz + cur[1] * g.rz + cur[2];
+    const int idstep[3] = {stp[0] * g.ry * g.rz, stp[1] * g.rz, stp[2]};
+    int diff[3] = {ovf[0] - cur[0], ovf[1] - cur[1], ovf[2] - cur[2]};
 
     while (limit <= 0 || n_samples < limit) {  // grid.cu:184
-      float t_traverse = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
-      const int64_t cell_id = (int64_t)(cur[0] * g.ry * g.rz + cur[1] * g.rz + cur[2]) + level_base;
-      if (!g.binaries[cell_id]) {
+      const float t_traverse = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
+      if (!lvl_bin[cid]) {
         if (step_size <= 0.0f) {
           t_last = t_traverse;
         } else {
@@ -191,15 +196,15 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
           if (t_next >= t_traverse) break;
         }
       }
-      // single_traversal, include/utils_grid.cuh:116-142
-      int a;
-      if ((tdist[0] < tdist[1]) && (tdist[0] < tdist[2])) a = 0;
-      else if (tdist[1] < tdist[2]) a = 1;
-      else a = 2;
-      // (dynamic indexing on 3-element register arrays: resolved with selects)
-      if (a == 0) { cur[0] += stp[0]; tdist[0] = __fadd_rn(tdist[0], delta[0]); if (cur[0] == ovf[0]) break; }
-      else if (a == 1) { cur[1] += stp[1]; tdist[1] = __fadd_rn(tdist[1], delta[1]); if (cur[1] == ovf[1]) break; }
-      else { cur[2] += stp[2]; tdist[2] = __fadd_rn(tdist[2], delta[2]); if (cur[2] == ovf[2]) break; }
+      // single_traversal, include/utils_grid.cuh:116-142: step along the axis with the nearest boundary.
+      // Three tiny predicated bodies instead of a three-way branch (the lanes of a warp pick different axes).
+      const bool m0 = (tdist[0] < tdist[1]) && (tdist[0] < tdist[2]);
+      const bool m1 = !m0 && (tdist[1] < tdist[2]);
+      const bool m2 = !m0 && !m1;
+      if (m0) { tdist[0] = __fadd_rn(tdist[0], delta[0]); diff[0] -= stp[0]; cid += idstep[0]; }
+      if (m1) { tdist[1] = __fadd_rn(tdist[1], delta[1]); diff[1] -= stp[1]; cid += idstep[1]; }
+      if (m2) { tdist[2] = __fadd_rn(tdist[2], delta[2]); diff[2] -= stp[2]; cid += idstep[2]; }
+      if ((m0 ? diff[0] : (m1 ? diff[1] : diff[2])) == 0) break;
     }
   }
   t_term = t_last;

@@ -120,7 +120,7 @@ struct LocalSink {
 // One thread per live ray: march up to n samples from the ray's previous terminate plane and
 // append them to the compact per-iteration sample list (warp-aggregated reservation keeps the
 // samples of neighbouring rays adjacent, which is what gives the hash-grid gather its locality).
-__global__ void __launch_bounds__(256) render_march_kernel(const int* counters_in, int rays_per_call,
+__global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counters_in, int rays_per_call,
                                                            const int* __restrict__ alive, const int* __restrict__ n_samp,
                                                            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                            GridView g, const float* __restrict__ t_min,
@@ -417,6 +417,9 @@ __global__ void __launch_bounds__(128, 6) render_composite_kernel(
           opac = __fadd_rn(opac, tm.w);
           depth = __fadd_rn(depth, __fmul_rn(tm.w, tm.tmid));
         }
+        // a ray whose samples were all filtered by alpha_thre leaves its state untouched: skip the
+        // read-modify-write of the 38 state planes (half of this kernel's traffic in free space)
+        if (n_vis > 0) {
         if (PROB) {  // variance terms against the UPDATED running rgb / depth
           float rv[3] = {st[ST_RGBVAR * NR], st[(ST_RGBVAR + 1) * NR], st[(ST_RGBVAR + 2) * NR]};
           float dv = st[ST_DVAR * NR];
@@ -463,6 +466,7 @@ __global__ void __launch_bounds__(128, 6) render_composite_kernel(
           for (int c = 0; c < 16; ++c)
             if (16 * g + c < n_sem) st[(ST_SEM + 16 * g + c) * NR] = acc[c];
         }
+        }  // n_vis > 0
       }
       const int n = n_samp[call];
       keep = (n > 0) && (opac <= opc_thre) && (k == n) && (iter_samples[call] < max_samples);

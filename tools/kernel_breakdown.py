@@ -65,6 +65,9 @@ print("field launches of member 0 (rows, live rays, ms, G rows/s):")
 rows = [(int(c[0]), int(c[1]), a.elapsed_time(b)) for name, a, b, c in evs if c is not None]
 for r, l, ms in rows[: len(rows) // 2]:
     print(f"  {r:9d} {l:8d} {ms:8.3f} {r / ms / 1e6 if ms > 0 else 0:6.2f}")
+for key in ("apnerf_render_march", "apnerf_render_composite"):
+    series = [a.elapsed_time(b) for name, a, b, _ in evs if name == key]
+    print(key, "ms per launch, member 0:", " ".join(f"{v:.3f}" for v in series[: len(series) // 2][:24]))
 scorer.interleave = True
 t0.record()
 for _ in range(5):
