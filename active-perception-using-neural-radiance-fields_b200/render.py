@@ -109,7 +109,7 @@ class FusedRenderer:
                rays_per_call: int, *, max_samples: int = 1024, near_plane: float = 0.0, far_plane: float = 1e10,
                render_step_size: float = 1e-3, cone_angle: float = 0.0, alpha_thre: float = 0.0,
                early_stop_eps: float = 1e-4, probabilistic: bool = True, state: Optional[Tensor] = None,
-               poll_every: int = 8, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False):
+               poll_every: int = 4, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False):
         """Render n_rays = n_calls * rays_per_call rays into the state [9 + C, n_rays] (un-finalised: see
         ``finalize``).  A generator: it enqueues one marching iteration on the CURRENT stream per ``next()``
         and yields the state tensor, so a caller can interleave several renders on different streams.
@@ -118,6 +118,7 @@ class FusedRenderer:
         iterations) to stop enqueuing once every ray has terminated."""
         import ctypes
 
+        ahead = 2
         require_cuda(rays_o, rays_d, estimator.binaries)
         assert estimator.binaries.shape[0] == 1, "the fused renderer handles single-level occupancy grids"
         assert radiance_field.num_semantic_classes == self.n_sem
@@ -202,8 +203,8 @@ class FusedRenderer:
                     ev = torch.cuda.Event()
                     ev.record()
                     events.append((it, ev))
-                    if len(events) > 2:  # throttle: never run more than two polls ahead of the device
-                        events[-3][1].synchronize()
+                    if len(events) > ahead:  # throttle: never run more than `ahead` polls ahead of the device
+                        events[-1 - ahead][1].synchronize()
                     finished = False
                     while events and events[0][1].query():
                         j, _ = events.pop(0)
