@@ -243,3 +243,50 @@ def probablistic_uncertainty(radiance_fields, estimators, trajectory, *, img_w, 
 
 
 _SCORERS = {}
+
+
+def trajector_uncertainty(radiance_fields, estimators, trajectory, step, *, img_w, img_h, focal, near_plane,
+                          render_step_size, cone_angle, alpha_thre, scale=0.1, device="cuda:0", log=None):
+    """Drop-in for the body of the older scorer ActiveNeRFMapper.trajector_uncertainty (pipeline.py:800-916),
+    used by the "random" policy: ensemble variance of rgb / depth, inverse opacity and (first member only)
+    semantic entropy per view, clipped and summed.  Returns ``(uncertainty, max_idx)``; appends the logged
+    per-view terms to ``log``.  The renders come from the device-driven renderer in one batch; the reduction is
+    the reference's float64 numpy, line for line (it is tiny: 40 views of 1 % resolution).
+
+    Reference quirk kept out: its tuple unpacking (4 names for member 0 at :823, 3 names for the others at
+    :842) only works for ONE member with semantic classes and raises otherwise; here every ensemble shape
+    is accepted and only the first member's semantics are used, as the reference intends."""
+    from .data_proc import Dataset
+
+    num_sample = 40
+    trajectory = np.asarray(trajectory)
+    unc_idx = uncertainty_view_indices(len(trajectory))
+    rendered, depths, accs, sems = [], [], [], []
+    for m, (f, e) in enumerate(zip(radiance_fields, estimators)):
+        out = Dataset.render_image_from_pose(f, e, trajectory[unc_idx], img_w, img_h, focal, near_plane,
+                                             render_step_size, scale, cone_angle, alpha_thre, 4, device)
+        rendered.append(out[0][-num_sample:])
+        depths.append(out[1][-num_sample:])
+        accs.append(out[2][-num_sample:])
+        if m == 0 and len(out) > 3:
+            sems.append(out[3][-num_sample:])
+    rendered, depths = np.array(rendered), np.array(depths)
+    acc0 = np.array(accs[0]) + 1e-4
+    intensity_var = np.mean(np.var(rendered, axis=0), axis=-1)
+    depth_var = np.var(depths, axis=0)
+    intensity_var_mean = np.clip(np.mean(intensity_var, axis=(1, 2)) * 4000, 0, 100)
+    depth_var_mean = np.clip(np.mean(depth_var, axis=(1, 2)) * 50, 0, 100)
+    acc_inv_mean = np.mean(np.clip(1 / acc0 - 1, 0, 10000), axis=(1, 2))
+    terms = [intensity_var_mean[-num_sample:], depth_var_mean[-num_sample:], acc_inv_mean[-num_sample:]]
+    uncertainty = intensity_var_mean + depth_var_mean + acc_inv_mean
+    if radiance_fields[0].num_semantic_classes > 0:
+        sem_p = torch.softmax(torch.from_numpy(np.array(sems)), dim=-1).numpy()
+        sem_entropy = -np.sum(sem_p * np.log(sem_p + 1e-10), axis=-1)
+        sem_entropy_mean = np.clip(np.mean(sem_entropy, axis=(0, 2, 3)) * 50, 0, 100)
+        uncertainty = uncertainty + sem_entropy_mean
+        terms.append(sem_entropy_mean[-num_sample:])
+    max_idx = np.sort(np.argsort(uncertainty))
+    uncertainty = np.mean(uncertainty[-11:]) if step == -1 else np.mean(uncertainty[max_idx])
+    if log is not None:
+        log.append(terms)
+    return uncertainty, max_idx

@@ -318,6 +318,27 @@ def main_sampling():
     out["upd_occs"], out["upd_binaries"] = eu.occs.numpy(), eu.binaries.numpy()
     print("update: occupied", int(eu.binaries.sum()), "of", eu.binaries.numel())
 
+    # ---- S5: Dataset.render_image_from_pose (habitat_to_data.py:304-411) and the older scorer
+    # ActiveNeRFMapper.trajector_uncertainty (pipeline.py:800-916).  The reference's own tuple unpacking (:823 wants
+    # 4 values from member 0, :842 wants 3 from the others) only works for ONE member with semantic classes, so
+    # that is the configuration pinned here.
+    traj = synthetic.make_poses(22, seed=CFG["pose_seed"] + 1)
+    focal = CFG["img_w"] / 2.0
+    res = Dataset.render_image_from_pose(field, e1, traj[:3], CFG["img_w"], CFG["img_h"], focal, CFG["near_plane"],
+                                         CFG["render_step_size"], CFG["scale"], CFG["cone_angle"], CFG["alpha_thre"], 4, "cpu")
+    for name, v in zip(("rgb", "depth", "acc", "sem"), res):
+        out[f"pose_{name}"] = v.astype(np.float32)
+    ns = dict(np=np, torch=torch, F=torch.nn.functional, Dataset=Dataset)
+    exec(reference_method(f"{REF}/scripts/pipeline.py", "ActiveNeRFMapper", "trajector_uncertainty"), ns)
+    me = types.SimpleNamespace(
+        config_file=dict(n_ensembles=1, cuda="cpu", img_w=CFG["img_w"], img_h=CFG["img_h"], near_plane=CFG["near_plane"],
+                         render_step_size=CFG["render_step_size"], cone_angle=CFG["cone_angle"], alpha_thre=CFG["alpha_thre"]),
+        radiance_fields=[field], estimators=[e1], focal=focal, trajector_uncertainty_list=[[]])
+    unc, max_idx = ns["trajector_uncertainty"](me, traj, 1)
+    out["legacy_poses"], out["legacy_uncertainty"], out["legacy_max_idx"] = traj, np.float64(unc), max_idx
+    out["legacy_terms"] = np.asarray(me.trajector_uncertainty_list[0][0], np.float64)
+    print("legacy scorer:", unc, out["legacy_terms"].shape)
+
     dst = os.path.join(HERE, "reference_python_ops.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
