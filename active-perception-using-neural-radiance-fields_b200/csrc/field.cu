@@ -160,6 +160,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   io.state = nullptr, io.n_rays_total = 0, io.rays_per_call = 1, io.alpha_thre = 0.f, io.opc_thre = 0.f;
   io.n_samp = nullptr, io.iter_samples = nullptr, io.max_samples = 0, io.s_cnt = nullptr, io.keep_flag = nullptr;
   io.total_samples = nullptr, io.probabilistic = 0;
+  io.cell_ids = nullptr, io.jitter = nullptr, io.occs_old = nullptr, io.occs_new = nullptr;
   HashGridMeta m;
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward: bad level table");
   FieldConst fc;
@@ -174,6 +175,42 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
 }
 
 APNERF_API int apnerf_field_weight_bytes(void) { return W_BYTES; }
+
+// OccGridEstimator._update for one grid level in one launch: jittered cell -> density -> EMA-max.
+APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const float* jitter,
+                                 const float* level_aabb_host, int rx, int ry, int rz, const float* occs_old,
+                                 float* occs_new, float occ_scale, float ema_decay, const float* aabb_host,
+                                 int n_levels, const uint32_t* meta_host, const void* table, const void* weights,
+                                 void* stream) {
+  if (n == 0) return 0;
+  APNERF_REQUIRE(cell_ids && jitter && occs_old && occs_new, "occ_update: null buffer");
+  APNERF_REQUIRE(occs_old != occs_new, "occ_update: occs_old must be a snapshot (cells may repeat)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    attr_set = true;
+  }
+  FieldIO io;
+  memset(&io, 0, sizeof(io));
+  io.n = n, io.density_only = 1;
+  io.table = (const uint2*)table, io.weights = (const uint4*)weights;
+  io.cell_ids = cell_ids, io.jitter = jitter, io.occs_old = occs_old, io.occs_new = occs_new;
+  io.occ_scale = occ_scale, io.ema_decay = ema_decay;
+  io.cell_res[0] = rx, io.cell_res[1] = ry, io.cell_res[2] = rz;
+  for (int a = 0; a < 3; ++a) {
+    io.cell_lo[a] = level_aabb_host[a];
+    io.cell_ext[a] = level_aabb_host[3 + a] - level_aabb_host[a];  // fp32, as aabbs[lvl, 3:] - aabbs[lvl, :3]
+  }
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "occ_update: bad level table");
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
+  const long long tiles = (n + TILE_M - 1) / TILE_M;
+  const int sms = apnerf_num_sms();
+  field_forward_kernel<<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  APNERF_CHECK_LAUNCH("field_forward_kernel(occ_update)");
+  return 0;
+}
 
 // Field query of the device-driven renderer with the compositor fused into the epilogue: sample
 // rows (s_ray, s_cnt, s_ts, s_te; *n_rows_dev rows, a multiple of 128, rays never straddle a tile)

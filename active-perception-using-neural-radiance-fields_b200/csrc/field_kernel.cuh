@@ -101,6 +101,15 @@ struct FieldIO {
   uint8_t* keep_flag;           // [n_rays_total] out: ray stays live for the next iteration
   int* total_samples;           // [n_calls] composited (alpha_thre-visible) samples
   int probabilistic;            // accumulate the variance terms
+  // --- occupancy-grid update (OccGridEstimator._update, occ_grid.py:377-437): the points are jittered cells
+  // of one grid level and the epilogue applies the EMA-max directly, density_only = 1 ---
+  const long long* cell_ids;    // [n] cell index inside the level (x slowest, as grid_coords)
+  const float* jitter;          // [n, 3] U[0,1) offsets inside the cell
+  float cell_lo[3], cell_ext[3];
+  int cell_res[3];
+  const float* occs_old;        // [cells] snapshot of the level's occupancy values
+  float* occs_new;              // [cells] updated in place of the snapshot's values
+  float occ_scale, ema_decay;   // occ = density * occ_scale;  new = max(old * ema_decay, occ)
 };
 
 __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bits) {
@@ -138,7 +147,17 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_smem, ui
 }
 
 __device__ __forceinline__ void sample_point(const FieldIO& io, long long s, float p[3], float d[3], bool want_dir) {
-  if (io.positions) {
+  if (io.cell_ids) {
+    // x = (grid_coords + rand) / resolution;  x = aabb_lo + x * (aabb_hi - aabb_lo)   (occ_grid.py:398-403)
+    const long long id = io.cell_ids[s];
+    const int yz = io.cell_res[1] * io.cell_res[2];
+    const int c[3] = {(int)(id / yz), (int)((id / io.cell_res[2]) % io.cell_res[1]), (int)(id % io.cell_res[2])};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float u = __fdiv_rn(__fadd_rn((float)c[a], io.jitter[3 * s + a]), (float)io.cell_res[a]);
+      p[a] = __fadd_rn(io.cell_lo[a], __fmul_rn(u, io.cell_ext[a]));
+    }
+  } else if (io.positions) {
     p[0] = io.positions[3 * s], p[1] = io.positions[3 * s + 1], p[2] = io.positions[3 * s + 2];
     if (want_dir) d[0] = io.directions[3 * s], d[1] = io.directions[3 * s + 1], d[2] = io.directions[3 * s + 2];
   } else {
@@ -462,7 +481,15 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
           inside = inside && (xa > 0.0f) && (xa < 1.0f);
         }
         // density = exp(x - 1) * selector  (ngp.py:79,191-193; fp16 network output upcast first)
-        if (io.density) io.density[s] = inside ? expf(__fsub_rn(__half2float(hb[0]), 1.0f)) : 0.0f;
+        const float dens = inside ? expf(__fsub_rn(__half2float(hb[0]), 1.0f)) : 0.0f;
+        if (io.density) io.density[s] = dens;
+        if (io.occs_new) {
+          // occs[cell] = maximum(occs[cell] * ema_decay, occ); a NaN result restores the old value (:405-434)
+          const long long id = io.cell_ids[s];
+          const float old = io.occs_old[id];
+          const float od = __fmul_rn(old, io.ema_decay), v = __fmul_rn(dens, io.occ_scale);
+          io.occs_new[id] = (od != od || v != v) ? old : fmaxf(od, v);
+        }
         if (io.feat) {
 #pragma unroll
           for (int i = 0; i < 15; ++i) io.feat[s * 15 + i] = hb[1 + i];

@@ -1,3 +1,3 @@
-from .occ_grid import OccGridEstimator
+from .occ_grid import DensityOccEvalFn, OccGridEstimator
 
-__all__ = ["OccGridEstimator"]
+__all__ = ["OccGridEstimator", "DensityOccEvalFn"]

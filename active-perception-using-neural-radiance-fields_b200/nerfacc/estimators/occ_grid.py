@@ -14,6 +14,20 @@ from ..grid import _enlarge_aabb, traverse_grids
 from ..volrend import render_visibility_from_alpha, render_visibility_from_density
 
 
+class DensityOccEvalFn:
+    """The pipeline's ``occ_eval_fn`` (scripts/pipeline.py:376-378: ``query_density(x) * render_step_size``) as an
+    object.  It is an ordinary callable, so it can be handed to any estimator; ``OccGridEstimator._update``
+    recognises it and runs the whole per-level body -- jittered cell -> density -> EMA-max -- as ONE launch of the
+    field kernel (``apnerf_occ_update``) instead of ~10 tensor ops around a density query."""
+
+    def __init__(self, radiance_field, render_step_size: float):
+        self.radiance_field = radiance_field
+        self.render_step_size = float(render_step_size)
+
+    def __call__(self, x: Tensor) -> Tensor:
+        return self.radiance_field.query_density(x) * self.render_step_size
+
+
 class OccGridEstimator(torch.nn.Module):
     DIM: int = 3
 
@@ -129,6 +143,28 @@ class OccGridEstimator(torch.nn.Module):
         return out
 
     @torch.no_grad()
+    def _update_level_fused(self, lvl: int, indices: Tensor, jitter: Tensor, backup: Tensor,
+                            occ_eval_fn: DensityOccEvalFn, ema_decay: float) -> None:
+        """occ_grid.py:396-434 for one level in one kernel (csrc/field_kernel.cuh, occupancy-update mode)."""
+        import ctypes
+
+        import numpy as np
+
+        from ..._lib import call
+
+        f = occ_eval_fn.radiance_field
+        weights, table = f._packed()
+        aabb_host = np.asarray(f.aabb.detach().cpu().numpy(), dtype=np.float32)
+        lvl_aabb = np.ascontiguousarray(self.aabbs[lvl].detach().cpu().numpy(), dtype=np.float32)
+        res = [int(v) for v in self.resolution.tolist()]
+        lo, hi = lvl * self.cells_per_lvl, (lvl + 1) * self.cells_per_lvl
+        with torch.cuda.device(self.occs.device):
+            call("apnerf_occ_update", int(indices.numel()), indices.contiguous(), jitter.contiguous(),
+                 lvl_aabb.ctypes.data_as(ctypes.c_void_p), res[0], res[1], res[2], backup[lo:hi], self.occs[lo:hi],
+                 float(occ_eval_fn.render_step_size), float(ema_decay), aabb_host.ctypes.data_as(ctypes.c_void_p),
+                 f.n_levels, f._meta.ctypes.data_as(ctypes.c_void_p), table, weights)
+
+    @torch.no_grad()
     def _update(self, step: int, occ_eval_fn: Callable, occ_thre: float = 0.01, ema_decay: float = 0.95,
                 warmup_steps: int = 256) -> None:
         """EMA-max occupancy update + binarisation, occ_grid.py:377-437 (incl. the fork's NaN
@@ -137,11 +173,17 @@ class OccGridEstimator(torch.nn.Module):
             lvl_indices = self._get_all_cells()
         else:
             lvl_indices = self._sample_uniform_and_occupied_cells(self.cells_per_lvl // 4)
+        fused = (isinstance(occ_eval_fn, DensityOccEvalFn) and hasattr(occ_eval_fn.radiance_field, "_packed")
+                 and self.occs.is_cuda)
         for lvl, indices in enumerate(lvl_indices):
             grid_coords = self.grid_coords[indices]
-            x = (grid_coords + torch.rand_like(grid_coords, dtype=torch.float32)) / self.resolution
-            x = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
+            jitter = torch.rand_like(grid_coords, dtype=torch.float32)
             backup = torch.clone(self.occs)
+            if fused:
+                self._update_level_fused(lvl, indices, jitter, backup, occ_eval_fn, ema_decay)
+                continue
+            x = (grid_coords + jitter) / self.resolution
+            x = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])
             occ = occ_eval_fn(x).squeeze(-1)
             cell_ids = lvl * self.cells_per_lvl + indices
             self.occs[cell_ids] = torch.maximum(self.occs[cell_ids] * ema_decay, occ)

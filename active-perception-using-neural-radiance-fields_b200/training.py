@@ -12,6 +12,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn.functional as F
 
+from .nerfacc import DensityOccEvalFn
 from .render import Rays, render_image_with_occgrid_with_depth_guide
 
 
@@ -52,10 +53,10 @@ def training_step(radiance_field, estimator, optimizer, batch: Dict[str, torch.T
     radiance_field.train()
     estimator.train()
     if update_occupancy:
-        def occ_eval_fn(x):
-            with torch.no_grad():
-                return radiance_field.query_density(x) * render_step_size
-        estimator.update_every_n_steps(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre)
+        # pipeline.py:376-378 as a recognisable object: the estimator fuses the whole per-level update into
+        # one launch of the field kernel (apnerf_occ_update)
+        estimator.update_every_n_steps(step=step, occ_eval_fn=DensityOccEvalFn(radiance_field, render_step_size),
+                                       occ_thre=occ_thre)
     out = render_image_with_occgrid_with_depth_guide(
         radiance_field, estimator, batch["rays"], near_plane=near_plane, render_step_size=render_step_size,
         render_bkgd=batch.get("color_bkgd"), cone_angle=cone_angle, alpha_thre=alpha_thre, depth=batch.get("dep"))

@@ -128,6 +128,18 @@ int apnerf_field_forward(long long n, const int* n_dev, const float* positions, 
                          void* feat, void* packed, int density_only, long long max_tiles, void* stream);
 int apnerf_field_weight_bytes(void);
 
+/* OccGridEstimator._update -- perception/nerfacc/nerfacc/estimators/occ_grid.py:377-437, the per-level body
+ * fused into the field kernel: x = level_aabb_lo + ((grid_coords(cell) + jitter) / res) * extent; occ =
+ * query_density(x) * occ_scale (the pipeline's occ_eval_fn, scripts/pipeline.py:470-475); occs_new[cell] =
+ * maximum(occs_old[cell] * ema_decay, occ), keeping occs_old[cell] where that is NaN (:405, :430-434).
+ * cell_ids i64 [n] (cells may repeat: occs_old must be a snapshot, the survivor is unspecified like the
+ * reference's indexed assignment), jitter f32 [n,3], level_aabb_host HOST float[6]. */
+int apnerf_occ_update(long long n, const long long* cell_ids, const float* jitter,
+                      const float* level_aabb_host, int rx, int ry, int rz, const float* occs_old,
+                      float* occs_new, float occ_scale, float ema_decay, const float* aabb_host,
+                      int n_levels, const uint32_t* meta_host, const void* table, const void* weights,
+                      void* stream);
+
 /* Training side of the hash grid (tcnn HashGrid backward, reached from loss.backward() at
  * scripts/pipeline.py:518): d_table [entries,4] fp32 += sum over samples/corners of
  * w_corner * d_enc [n, n_levels*4] fp32 (vector atomics). */

@@ -182,3 +182,46 @@ def test_train_mode_render_shapes_and_eval_chunking(apnerf):
     assert rgb.shape == (20, 30, 3) and acc.shape == (20, 30, 1) and depth.shape == (20, 30, 1)
     assert sem.shape == (20, 30, 29) and n > 0
     assert torch.isfinite(rgb).all() and (acc >= 0).all() and (acc <= 1 + 1e-5).all()
+
+
+def test_fused_occupancy_update_matches_op_by_op(apnerf):
+    """apnerf_occ_update (jittered cell -> density -> EMA-max in the field kernel) against the op-by-op body of
+    OccGridEstimator._update (occ_grid.py:377-437) with the same random numbers: bit-identical occupancy values
+    and binaries in the warm-up branch (every visible cell once), and in the sampled branch everywhere except
+    cells drawn more than once (the reference's indexed assignment keeps an unspecified one of them)."""
+    from apnerf import synthetic
+    from apnerf.nerfacc import DensityOccEvalFn
+
+    field = _field(apnerf)
+    step_size = 5e-3
+
+    def run(fused, steps):
+        est = apnerf.OccGridEstimator(synthetic.ROI_AABB, resolution=64, levels=2).to(DEV).train()
+        est.occs[3::17] = -1.0  # cells no camera sees are never touched
+        fn = DensityOccEvalFn(field, step_size)
+        plain = (lambda x: field.query_density(x) * step_size)
+        drawn = []
+        sample = est._sample_uniform_and_occupied_cells
+        est._sample_uniform_and_occupied_cells = lambda n: drawn.append(sample(n)) or drawn[-1]
+        torch.manual_seed(123)
+        for step in steps:
+            est.update_every_n_steps(step=step, occ_eval_fn=fn if fused else plain, occ_thre=1e-2)
+        return est.occs.clone(), est.binaries.clone(), drawn
+
+    with torch.no_grad():
+        a_occ, a_bin, _ = run(True, (0, 16))
+        b_occ, b_bin, _ = run(False, (0, 16))
+    assert torch.equal(a_occ, b_occ) and torch.equal(a_bin, b_bin)
+    assert 0 < int(a_bin.sum()) < a_bin.numel() and bool((a_occ[3::17] == -1.0).all())
+    with torch.no_grad():
+        a_occ, a_bin, a_drawn = run(True, (0, 256))
+        b_occ, b_bin, b_drawn = run(False, (0, 256))
+    cells = a_occ.numel() // 2
+    once = torch.ones_like(a_occ, dtype=torch.bool)
+    for lvl, (ia, ib) in enumerate(zip(a_drawn[0], b_drawn[0])):
+        assert torch.equal(ia, ib)  # same random stream on both paths
+        counts = torch.bincount(ia, minlength=cells)
+        once[lvl * cells:(lvl + 1) * cells] = counts <= 1
+    assert 0.5 < once.float().mean().item() < 1.0
+    assert torch.equal(a_occ[once], b_occ[once])
+    assert (a_bin == b_bin).float().mean().item() >= 0.98
