@@ -3,6 +3,7 @@
 // Replaces tcnn.NetworkWithInputEncoding / tcnn.Network / tcnn.Encoding as used by
 // NGPRadianceField (perception/models/radiance_fields/ngp.py:107-238).
 #include "field_kernel.cuh"
+#include "field_bwd_kernel.cuh"
 
 namespace apnerf {
 
@@ -146,7 +147,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward: at most 32 semantic classes");
   static bool attr_set = false;
   if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
     attr_set = true;
   }
   FieldIO io;
@@ -161,6 +162,8 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   io.n_samp = nullptr, io.iter_samples = nullptr, io.max_samples = 0, io.s_cnt = nullptr, io.keep_flag = nullptr;
   io.total_samples = nullptr, io.probabilistic = 0;
   io.cell_ids = nullptr, io.jitter = nullptr, io.occs_old = nullptr, io.occs_new = nullptr;
+  io.save_enc = io.save_h1 = io.save_h2 = io.save_xh = io.save_xs = nullptr;
+  io.save_hh1 = io.save_hh2 = io.save_hs1 = io.save_hs2 = nullptr;
   HashGridMeta m;
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward: bad level table");
   FieldConst fc;
@@ -169,12 +172,83 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   if (tiles < 1) tiles = 1;
   const int sms = apnerf_num_sms();
   const int grid = (int)(tiles < sms ? tiles : sms);
-  field_forward_kernel<<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  field_forward_kernel<false><<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
   APNERF_CHECK_LAUNCH("field_forward_kernel");
   return 0;
 }
 
 APNERF_API int apnerf_field_weight_bytes(void) { return W_BYTES; }
+
+// Training forward: the same kernel with raw outputs (fp16 logits upcast) and every activation the backward
+// needs written out as row-major fp16.  save: [enc 64 | h1 128 | h2 128 | xh 32 | xs 16 | hh1 64 | hh2 64 |
+// hs1 64 | hs2 64] = nine pointers.
+APNERF_API int apnerf_field_forward_train(long long n, const float* positions, const float* directions,
+                                          const float* aabb_host, int n_levels, const uint32_t* meta_host,
+                                          const void* table, const void* weights, float* dens_logit,
+                                          float* rgb_logit, float* sem_logit, int n_sem, void* save_enc,
+                                          void* save_h1, void* save_h2, void* save_xh, void* save_xs,
+                                          void* save_hh1, void* save_hh2, void* save_hs1, void* save_hs2,
+                                          void* stream) {
+  if (n == 0) return 0;
+  APNERF_REQUIRE(positions && directions && dens_logit && rgb_logit, "field_forward_train: null buffer");
+  APNERF_REQUIRE(save_enc && save_h1 && save_h2 && save_xh && save_xs && save_hh1 && save_hh2 && save_hs1 && save_hs2,
+                 "field_forward_train: all nine activation buffers are required");
+  APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward_train: at most 32 semantic classes");
+  static bool attr_set = false;
+  if (!attr_set) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    attr_set = true;
+  }
+  FieldIO io;
+  memset(&io, 0, sizeof(io));
+  io.n = n, io.positions = positions, io.directions = directions;
+  io.table = (const uint2*)table, io.weights = (const uint4*)weights;
+  io.density = dens_logit, io.rgb = rgb_logit, io.rgb_row = 3, io.rgb_ch = 1;
+  io.sem = sem_logit, io.sem_row = n_sem, io.sem_ch = 1, io.n_sem = sem_logit ? n_sem : 0;
+  io.rays_per_call = 1;
+  io.save_enc = (__half*)save_enc, io.save_h1 = (__half*)save_h1, io.save_h2 = (__half*)save_h2;
+  io.save_xh = (__half*)save_xh, io.save_xs = (__half*)save_xs, io.save_hh1 = (__half*)save_hh1;
+  io.save_hh2 = (__half*)save_hh2, io.save_hs1 = (__half*)save_hs1, io.save_hs2 = (__half*)save_hs2;
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward_train: bad level table");
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
+  const long long tiles = (n + TILE_M - 1) / TILE_M;
+  const int sms = apnerf_num_sms();
+  field_forward_kernel<true><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  APNERF_CHECK_LAUNCH("field_forward_kernel(train)");
+  return 0;
+}
+
+// Backward of the three MLPs (csrc/field_bwd_kernel.cuh).  weights_t: the blob of apnerf_field_forward with
+// every matrix transposed.  Outputs: g_* = activation gradients x loss_scale (fp16), d_enc fp32 unscaled.
+APNERF_API int apnerf_field_backward(long long n, const float* d_dens, const float* d_rgb, const float* d_sem,
+                                     int n_sem, const void* h1, const void* h2, const void* hh1, const void* hh2,
+                                     const void* hs1, const void* hs2, const void* weights_t, float loss_scale,
+                                     void* g_hh2, void* g_hs2, void* g_hh1, void* g_hs1, void* g_base, void* g_h2,
+                                     void* g_h1, float* d_enc, void* stream) {
+  if (n == 0) return 0;
+  APNERF_REQUIRE(d_dens && d_rgb && h1 && h2 && hh1 && hh2 && hs1 && hs2 && weights_t, "field_backward: null input");
+  APNERF_REQUIRE(g_hh2 && g_hs2 && g_hh1 && g_hs1 && g_base && g_h2 && g_h1 && d_enc, "field_backward: null output");
+  APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT && loss_scale > 0.f, "field_backward: bad n_sem / loss_scale");
+  static bool attr_set = false;
+  if (!attr_set) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr_set = true;
+  }
+  FieldBwdIO io;
+  io.n = n, io.d_dens = d_dens, io.d_rgb = d_rgb, io.d_sem = d_sem, io.n_sem = d_sem ? n_sem : 0;
+  io.h1 = (const __half*)h1, io.h2 = (const __half*)h2, io.hh1 = (const __half*)hh1, io.hh2 = (const __half*)hh2;
+  io.hs1 = (const __half*)hs1, io.hs2 = (const __half*)hs2, io.weights_t = (const uint4*)weights_t;
+  io.loss_scale = loss_scale;
+  io.g_hh2 = (__half*)g_hh2, io.g_hs2 = (__half*)g_hs2, io.g_hh1 = (__half*)g_hh1, io.g_hs1 = (__half*)g_hs1;
+  io.g_base = (__half*)g_base, io.g_h2 = (__half*)g_h2, io.g_h1 = (__half*)g_h1, io.d_enc = d_enc;
+  const long long tiles = (n + TILE_M - 1) / TILE_M;
+  const long long cap = 2LL * apnerf_num_sms();  // two 112 KB CTAs fit one SM: one's epilogue hides the other's MMAs
+  field_backward_kernel<<<(int)(tiles < cap ? tiles : cap), BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(io);
+  APNERF_CHECK_LAUNCH("field_backward_kernel");
+  return 0;
+}
 
 // OccGridEstimator._update for one grid level in one launch: jittered cell -> density -> EMA-max.
 APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const float* jitter,
@@ -187,7 +261,7 @@ APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const f
   APNERF_REQUIRE(occs_old != occs_new, "occ_update: occs_old must be a snapshot (cells may repeat)");
   static bool attr_set = false;
   if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
     attr_set = true;
   }
   FieldIO io;
@@ -207,7 +281,7 @@ APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const f
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const long long tiles = (n + TILE_M - 1) / TILE_M;
   const int sms = apnerf_num_sms();
-  field_forward_kernel<<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  field_forward_kernel<false><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
   APNERF_CHECK_LAUNCH("field_forward_kernel(occ_update)");
   return 0;
 }
@@ -226,7 +300,7 @@ APNERF_API int apnerf_field_forward_fused(const int* n_rows_dev, long long max_t
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward_fused: at most 32 semantic classes");
   static bool attr_set = false;
   if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
     attr_set = true;
   }
   FieldIO io;
@@ -243,7 +317,7 @@ APNERF_API int apnerf_field_forward_fused(const int* n_rows_dev, long long max_t
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const int sms = apnerf_num_sms();
   const int grid = (int)(max_tiles < 1 ? 1 : (max_tiles < sms ? max_tiles : sms));
-  field_forward_kernel<<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  field_forward_kernel<false><<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
   APNERF_CHECK_LAUNCH("field_forward_kernel(fused)");
   return 0;
 }

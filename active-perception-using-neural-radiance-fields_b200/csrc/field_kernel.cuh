@@ -101,6 +101,17 @@ struct FieldIO {
   uint8_t* keep_flag;           // [n_rays_total] out: ray stays live for the next iteration
   int* total_samples;           // [n_calls] composited (alpha_thre-visible) samples
   int probabilistic;            // accumulate the variance terms
+  // --- training forward (kernel instantiation TRAIN): density / rgb get the raw fp16 logits (no exp / sigmoid /
+  // selector) and the activations the backward kernel needs are saved (fp16, row-major) ---
+  __half* save_enc;             // [n, 64]
+  __half* save_h1;              // [n, 128]
+  __half* save_h2;              // [n, 128]
+  __half* save_xh;              // [n, 32]  head input  (16 SH | 15 geo | 1.0)
+  __half* save_xs;              // [n, 16]  semantic input (15 geo | 1.0)
+  __half* save_hh1;             // [n, 64]
+  __half* save_hh2;             // [n, 64]
+  __half* save_hs1;             // [n, 64]
+  __half* save_hs2;             // [n, 64]
   // --- occupancy-grid update (OccGridEstimator._update, occ_grid.py:377-437): the points are jittered cells
   // of one grid level and the epilogue applies the EMA-max directly, density_only = 1 ---
   const long long* cell_ids;    // [n] cell index inside the level (x slowest, as grid_coords)
@@ -120,7 +131,8 @@ __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bit
 
 // TMEM accumulator columns [col0, col0 + 32) of this thread's row -> ReLU -> fp16 -> the A tile
 // of the next layer (K-chunks col0/8 .. col0/8+3); `rows16` = TILE_M * 16 bytes per K-chunk.
-__device__ __forceinline__ void relu_store_32(uint32_t taddr, uint8_t* dst, int row, int col0) {
+__device__ __forceinline__ void relu_store_32(uint32_t taddr, uint8_t* dst, int row, int col0,
+                                              __half* save_row = nullptr) {
   uint32_t v[32];
   ptx::tmem_ld_x32(taddr + col0, v);
   ptx::tmem_wait_ld();
@@ -132,6 +144,7 @@ __device__ __forceinline__ void relu_store_32(uint32_t taddr, uint8_t* dst, int 
     q.z = pack_relu_h2(v[8 * j + 4], v[8 * j + 5]);
     q.w = pack_relu_h2(v[8 * j + 6], v[8 * j + 7]);
     *reinterpret_cast<uint4*>(dst + (col0 / 8 + j) * (TILE_M * 16) + row * 16) = q;
+    if (save_row) *reinterpret_cast<uint4*>(save_row + col0 + 8 * j) = q;
   }
 }
 
@@ -305,6 +318,8 @@ __device__ __forceinline__ void composite_tile(const FieldIO& io, const Composit
   chain_bar_sync(chain);  // every reader of the scratch is done before the next tile's activations overwrite it
 }
 
+template <bool TRAIN>  // TRAIN: raw outputs + saved activations (apnerf_field_forward_train); the inference
+                       // instantiation carries none of that code
 __global__ void __launch_bounds__(FIELD_THREADS, 1)
 field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst fc) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -376,8 +391,11 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       ptx::mbar_wait(bar_empty + 8 * buf, ph ^ 1);  // MMA of the tile that used this slot is done
       uint8_t* a0 = smem + SM_A0 + buf * (TILE_M * ENC_DIM * 2);
 #pragma unroll
-      for (int j = 0; j < LEVELS_PER_ENC_THREAD / 2; ++j)
+      for (int j = 0; j < LEVELS_PER_ENC_THREAD / 2; ++j) {
         *reinterpret_cast<uint4*>(a0 + (part * (LEVELS_PER_ENC_THREAD / 2) + j) * (TILE_M * 16) + row * 16) = q[j];
+        if (TRAIN && s < n)
+          reinterpret_cast<uint4*>(io.save_enc + s * ENC_DIM)[part * (LEVELS_PER_ENC_THREAD / 2) + j] = q[j];
+      }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar_full + 8 * buf);
     }
@@ -457,8 +475,11 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       for (int layer = 0; layer < 2; ++layer) {
         ptx::mbar_wait(my_mma, mma_ph), mma_ph ^= 1;
         ptx::tc_fence_after();
+        {
+          __half* save = (TRAIN && s < n) ? (layer == 0 ? io.save_h1 : io.save_h2) + s * HID : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < HID; c += 32) relu_store_32(trow + TM_MAIN, act, row, c);
+          for (int c = 0; c < HID; c += 32) relu_store_32(trow + TM_MAIN, act, row, c, save);
+        }
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         ptx::mbar_arrive(my_epi);
@@ -482,7 +503,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         }
         // density = exp(x - 1) * selector  (ngp.py:79,191-193; fp16 network output upcast first)
         const float dens = inside ? expf(__fsub_rn(__half2float(hb[0]), 1.0f)) : 0.0f;
-        if (io.density) io.density[s] = dens;
+        if (io.density) io.density[s] = TRAIN ? __half2float(hb[0]) : dens;
         if (io.occs_new) {
           // occs[cell] = maximum(occs[cell] * ema_decay, occ); a NaN result restores the old value (:405-434)
           const long long id = io.cell_ids[s];
@@ -515,6 +536,12 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(act + ACT_XH + j * (TILE_M * 16) + row * 16) = hq[j];
 #pragma unroll
         for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(act + ACT_XS + j * (TILE_M * 16) + row * 16) = hq[2 + j];
+        if (TRAIN && s < n) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(io.save_xh + s * HEAD_IN)[j] = hq[j];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) reinterpret_cast<uint4*>(io.save_xs + s * SEM_IN)[j] = hq[2 + j];
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
@@ -524,10 +551,12 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       for (int layer = 0; layer < 2; ++layer) {
         ptx::mbar_wait(my_mma, mma_ph), mma_ph ^= 1;
         ptx::tc_fence_after();
-        relu_store_32(trow + TM_H, act + ACT_HH, row, 0);
-        relu_store_32(trow + TM_H, act + ACT_HH, row, 32);
-        relu_store_32(trow + TM_S, act + ACT_HS, row, 0);
-        relu_store_32(trow + TM_S, act + ACT_HS, row, 32);
+        __half* save_h = (TRAIN && s < n) ? (layer == 0 ? io.save_hh1 : io.save_hh2) + s * HID2 : nullptr;
+        __half* save_s = (TRAIN && s < n) ? (layer == 0 ? io.save_hs1 : io.save_hs2) + s * HID2 : nullptr;
+        relu_store_32(trow + TM_H, act + ACT_HH, row, 0, save_h);
+        relu_store_32(trow + TM_H, act + ACT_HH, row, 32, save_h);
+        relu_store_32(trow + TM_S, act + ACT_HS, row, 0, save_s);
+        relu_store_32(trow + TM_S, act + ACT_HS, row, 32, save_s);
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         ptx::mbar_arrive(my_epi);
@@ -572,7 +601,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float v = __half2float(__float2half_rn(__uint_as_float(oh[c])));
-          io.rgb[c * io.rgb_ch + s * io.rgb_row] = 1.0f / (1.0f + expf(-v));
+          io.rgb[c * io.rgb_ch + s * io.rgb_row] = TRAIN ? v : 1.0f / (1.0f + expf(-v));
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c)

@@ -117,26 +117,96 @@ class _HashGridEncode(torch.autograd.Function):
         return None, d_table, None, None
 
 
-class _HalfLinear(torch.autograd.Function):
-    """y = round_fp16(x_fp16 @ W_fp16^T) with fp32 accumulation (what the fused kernel's tcgen05 layers
-    compute), optional ReLU; backward in fp32 through the rounding (straight-through)."""
+LOSS_SCALE = 128.0  # tcnn's default loss scale for fp16 networks
+
+
+class _FusedMLPs(torch.autograd.Function):
+    """The hash grid + three MLPs of the differentiable (training) path as two kernels:
+
+    forward   ``apnerf_field_forward_train`` -- the fused inference kernel, instantiated to emit the raw fp16
+              network outputs and to save every layer's activation;
+    backward  ``apnerf_field_backward`` (tcgen05 chain of dX = dY . W with the ReLU masks, gradients x LOSS_SCALE
+              in fp16 like tcnn) + ``apnerf_hashgrid_encode_bwd`` (scatter-add into the fp32 table gradient);
+              the weight gradients dW = dY^T . X are nine plain library GEMMs over all samples with fp32
+              accumulation, as tcnn computes them with CUTLASS.
+
+    Inputs: positions, directions [n, 3] f32 and the three flat fp32 parameter vectors.  Outputs: density
+    logit [n], rgb logits [n, 3], semantic logits [n, C] (fp16 values upcast)."""
 
     @staticmethod
-    def forward(ctx, x, w, relu):
-        xh, wh = x.to(torch.float16), w.to(torch.float16)
-        y = torch.matmul(xh, wh.t())
-        if relu:
-            y = torch.relu(y)
-        ctx.relu = relu
-        ctx.save_for_backward(xh, wh, y if relu else xh[:0])
-        return y.float()
+    def forward(ctx, pos, dirs, base_params, head_params, sem_params, field):
+        import ctypes
+
+        n = pos.shape[0]
+        dev = pos.device
+        C = field.num_semantic_classes
+        weights, table = field._packed()
+        f16 = dict(device=dev, dtype=torch.float16)
+        saves = [torch.empty((n, w), **f16) for w in (64, 128, 128, 32, 16, 64, 64, 64, 64)]
+        dens = torch.empty(n, device=dev, dtype=torch.float32)
+        rgb = torch.empty((n, 3), device=dev, dtype=torch.float32)
+        sem = torch.empty((n, C), device=dev, dtype=torch.float32) if C > 0 else None
+        aabb_host = np.asarray(field.aabb.detach().cpu().numpy(), dtype=np.float32)
+        if n:
+            with torch.cuda.device(dev):
+                call("apnerf_field_forward_train", n, pos, dirs, aabb_host.ctypes.data_as(ctypes.c_void_p),
+                     field.n_levels, field._meta.ctypes.data_as(ctypes.c_void_p), table, weights, dens, rgb, sem, C,
+                     *saves)
+        ctx.field = field
+        ctx.save_for_backward(pos, *saves)
+        if C > 0:
+            return dens, rgb, sem
+        return dens, rgb
 
     @staticmethod
-    def backward(ctx, g):
-        xh, wh, y = ctx.saved_tensors
-        if ctx.relu:
-            g = g * (y > 0)
-        return g @ wh.float(), g.t() @ xh.float(), None
+    def backward(ctx, g_dens, g_rgb, g_sem=None):
+        import ctypes
+
+        field = ctx.field
+        pos, enc, h1, h2, xh, xs, hh1, hh2, hs1, hs2 = ctx.saved_tensors
+        n = pos.shape[0]
+        dev = pos.device
+        C = field.num_semantic_classes
+        g_dens = (torch.zeros(n, device=dev) if g_dens is None else g_dens.float()).contiguous()
+        g_rgb = (torch.zeros((n, 3), device=dev) if g_rgb is None else g_rgb.float()).contiguous()
+        if C > 0:
+            g_sem = (torch.zeros((n, C), device=dev) if g_sem is None else g_sem.float()).contiguous()
+        else:
+            g_sem = None
+        f16 = dict(device=dev, dtype=torch.float16)
+        g_hh2, g_hs2, g_hh1, g_hs1 = (torch.empty((n, 64), **f16) for _ in range(4))
+        g_base = torch.empty((n, 16), **f16)
+        g_h2, g_h1 = torch.empty((n, 128), **f16), torch.empty((n, 128), **f16)
+        d_enc = torch.empty((n, 64), device=dev, dtype=torch.float32)
+        d_table = torch.zeros((field._n_entries, 4), device=dev, dtype=torch.float32)
+        if n:
+            aabb_min, aabb_max = torch.split(field.aabb, 3, dim=-1)
+            x01 = ((pos - aabb_min) / (aabb_max - aabb_min)).contiguous()
+            with torch.cuda.device(dev):
+                call("apnerf_field_backward", n, g_dens, g_rgb, g_sem, C, h1, h2, hh1, hh2, hs1, hs2,
+                     field._packed_t(), float(LOSS_SCALE), g_hh2, g_hs2, g_hh1, g_hs1, g_base, g_h2, g_h1, d_enc)
+                call("apnerf_hashgrid_encode_bwd", n, x01, field.n_levels,
+                     field._meta.ctypes.data_as(ctypes.c_void_p),
+                     d_enc[:, : field.n_levels * 4].contiguous(), d_table)
+
+        def wgrad(g, x, scaled=True):  # dW [out, in] = g^T . x over all samples, fp32 accumulation
+            w = g.float().t() @ x.float()
+            return w / LOSS_SCALE if scaled else w
+
+        def padded(g, rows):  # gradients of the zero-padded output rows are zero
+            out = torch.zeros((rows, g.shape[1]), device=dev, dtype=torch.float32)
+            out[: g.shape[0]] = g
+            return out
+
+        base_grad = torch.cat([wgrad(g_h1, enc).reshape(-1), wgrad(g_h2, h1).reshape(-1),
+                               wgrad(g_base, h2).reshape(-1), d_table.reshape(-1)])
+        head_grad = torch.cat([wgrad(g_hh1, xh).reshape(-1), wgrad(g_hh2, hh1).reshape(-1),
+                               padded(wgrad(g_rgb, hh2, scaled=False), 16).reshape(-1)])
+        sem_grad = None
+        if C > 0:
+            sem_grad = torch.cat([wgrad(g_hs1, xs).reshape(-1), wgrad(g_hs2, hs1).reshape(-1),
+                                  padded(wgrad(g_sem, hs2, scaled=False), 32).reshape(-1)])
+        return None, None, base_grad, head_grad, sem_grad, None
 
 
 class NGPRadianceField(torch.nn.Module):
@@ -239,6 +309,33 @@ class NGPRadianceField(torch.nn.Module):
             self._cache_key = key
         return self._cache
 
+    def _packed_t(self):
+        """The weight blob of ``_packed`` with every matrix transposed ([in, out], same UMMA layout and
+        offsets): the B operands of the backward kernel's dX = dY . W products."""
+        ps = [self.mlp_base.params, self.mlp_head.params] + ([self.mlp_sem.params] if self.num_semantic_classes > 0 else [])
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+        if getattr(self, "_cache_t", None) is not None and key == self._cache_t_key:
+            return self._cache_t
+        with torch.no_grad():
+            dev = self.mlp_base.params.device
+
+            def mats(flat, dims):
+                out, o = [], 0
+                for n_out, n_in in dims:
+                    w = flat[o:o + n_out * n_in].reshape(n_out, n_in).to(torch.float16)
+                    out.append(_umma_pack(w.t().contiguous()))
+                    o += n_out * n_in
+                return out
+
+            blobs = mats(self.mlp_base.params, self._base_dims) + mats(self.mlp_head.params, self._head_dims)
+            if self.num_semantic_classes > 0:
+                blobs += mats(self.mlp_sem.params, self._sem_dims)
+            else:
+                blobs += [torch.zeros(a * b, dtype=torch.float16, device=dev) for a, b in self._sem_dims]
+            self._cache_t = torch.cat(blobs).contiguous()
+            self._cache_t_key = key
+        return self._cache_t
+
     def _run(self, positions, directions, density_only, return_feat=False):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._run_with_grad(positions, directions, density_only, return_feat)
@@ -275,45 +372,33 @@ class NGPRadianceField(torch.nn.Module):
         return out
 
     def _run_with_grad(self, positions, directions, density_only, return_feat):
-        """Differentiable path (training): the hash-grid gather and its scatter-add backward are the
-        CUDA kernels behind the C-ABI; the small MLPs run as fp16 matmuls with the same rounding points
-        as the fused inference kernel and an fp32 backward.  Gradients reach the flat fp32 ``params``."""
+        """Differentiable path (training): ``_FusedMLPs`` (two tcgen05 kernels + the hash-grid scatter) gives
+        the raw network outputs; the activations of ngp.py:191-220 (trunc_exp, selector, sigmoid) are
+        elementwise torch ops on top, so autograd reaches the flat fp32 ``params``."""
         require_cuda(positions, directions, self.mlp_base.params)
-        pos = positions.reshape(-1, 3).to(torch.float32)
+        if return_feat:
+            raise NotImplementedError("query_density(return_feat=True) under autograd is not on the pipeline's path")
+        pos = positions.reshape(-1, 3).to(torch.float32).contiguous().detach()
+        if directions is None:  # query_density under autograd: the colour / semantic heads see a dummy direction
+            dirs = torch.zeros_like(pos)
+            dirs[:, 2] = 1.0
+        else:
+            dirs = directions.reshape(-1, 3).to(torch.float32).contiguous().detach()
         aabb_min, aabb_max = torch.split(self.aabb, 3, dim=-1)
-        x = ((pos - aabb_min) / (aabb_max - aabb_min)).detach()
+        x = (pos - aabb_min) / (aabb_max - aabb_min)
         selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
-        w1, w2, w3 = self._split(self.mlp_base.params[: self._n_base_w], self._base_dims)
-        table = self.mlp_base.params[self._n_base_w:].view(-1, 4)
-        enc = _HashGridEncode.apply(x, table, self._meta, self.n_levels)
-        h = _HalfLinear.apply(enc, w1, True)
-        h = _HalfLinear.apply(h, w2, True)
-        base = _HalfLinear.apply(h, w3, False)
-        density = self.density_activation(base[:, :1]) * selector[:, None]
-        feat = base[:, 1:1 + self.geo_feat_dim]
+        sem_params = self.mlp_sem.params if self.num_semantic_classes > 0 else None
+        out = _FusedMLPs.apply(pos, dirs, self.mlp_base.params, self.mlp_head.params, sem_params, self)
+        density = self.density_activation(out[0][:, None]) * selector[:, None]
         if density_only:
-            return density.reshape(-1), None, None, (feat if return_feat else None)
-        n = pos.shape[0]
-        dirs = directions.reshape(-1, 3).to(torch.float32).contiguous()
-        sh = torch.empty((n, 16), device=pos.device, dtype=torch.float16)
-        if n:
-            with torch.cuda.device(pos.device):
-                call("apnerf_sh4", n, dirs, sh)
-        ones = torch.ones((n, 1), device=pos.device, dtype=torch.float32)
-        wh1, wh2, wh3 = self._split(self.mlp_head.params, self._head_dims)
-        hh = _HalfLinear.apply(torch.cat([sh.float(), feat, ones], -1), wh1, True)
-        hh = _HalfLinear.apply(hh, wh2, True)
-        rgb = torch.sigmoid(_HalfLinear.apply(hh, wh3, False)[:, :3])
-        sem = None
-        if self.num_semantic_classes > 0:
-            ws1, ws2, ws3 = self._split(self.mlp_sem.params, self._sem_dims)
-            hs = _HalfLinear.apply(torch.cat([feat, ones], -1), ws1, True)
-            hs = _HalfLinear.apply(hs, ws2, True)
-            sem = _HalfLinear.apply(hs, ws3, False)[:, : self.num_semantic_classes]
-        return density.reshape(-1), rgb, sem, (feat if return_feat else None)
+            return density.reshape(-1), None, None, None
+        rgb = torch.sigmoid(out[1])
+        sem = out[2] if self.num_semantic_classes > 0 else None
+        return density.reshape(-1), rgb, sem, None
 
     def _apply(self, fn, *a, **k):
         self._cache = None
+        self._cache_t = None
         self._aabb_host = None
         return super()._apply(fn, *a, **k)
 

@@ -50,7 +50,7 @@ if rank == 0:
     print(json.dumps({"metric": "training rays/s (config 4)", "value": N_RAYS * world * STEPS / dt, "unit": "rays/s",
                       "n_gpus": world, "ms_per_step": 1e3 * dt / STEPS, "rays_per_batch_per_gpu": N_RAYS,
                       "mean_samples_per_step": n_samples / STEPS, "loss": out["loss"] if out else None,
-                      "note": "hash-grid fwd/bwd CUDA kernels + packed volrend CUDA fwd/bwd; MLP layers as fp16 "
-                              "library GEMMs (round-1 placeholder for a tcgen05 backward)"}))
+                      "note": "fused tcgen05 forward (activations saved) + tcgen05 backward chain + hash-grid scatter + "
+                              "packed volrend CUDA fwd/bwd; weight gradients dW = dY^T X as library GEMMs"}))
 if world > 1:
     dist.destroy_process_group()
