@@ -185,7 +185,8 @@ APNERF_API int apnerf_field_weight_bytes(void) { return W_BYTES; }
 APNERF_API int apnerf_field_forward_train(long long n, const float* positions, const float* directions,
                                           const float* aabb_host, int n_levels, const uint32_t* meta_host,
                                           const void* table, const void* weights, float* dens_logit,
-                                          float* rgb_logit, float* sem_logit, int n_sem, void* save_enc,
+                                          float* rgb_logit, float* sem_logit, int n_sem, long long save_stride,
+                                          void* save_enc,
                                           void* save_h1, void* save_h2, void* save_xh, void* save_xs,
                                           void* save_hh1, void* save_hh2, void* save_hs1, void* save_hs2,
                                           void* stream) {
@@ -206,6 +207,8 @@ APNERF_API int apnerf_field_forward_train(long long n, const float* positions, c
   io.density = dens_logit, io.rgb = rgb_logit, io.rgb_row = 3, io.rgb_ch = 1;
   io.sem = sem_logit, io.sem_row = n_sem, io.sem_ch = 1, io.n_sem = sem_logit ? n_sem : 0;
   io.rays_per_call = 1;
+  APNERF_REQUIRE(save_stride >= 128 && save_stride % 8 == 0, "field_forward_train: save_stride must be a multiple of 8, >= 128");
+  io.save_stride = save_stride;
   io.save_enc = (__half*)save_enc, io.save_h1 = (__half*)save_h1, io.save_h2 = (__half*)save_h2;
   io.save_xh = (__half*)save_xh, io.save_xs = (__half*)save_xs, io.save_hh1 = (__half*)save_hh1;
   io.save_hh2 = (__half*)save_hh2, io.save_hs1 = (__half*)save_hs1, io.save_hs2 = (__half*)save_hs2;
@@ -223,13 +226,17 @@ APNERF_API int apnerf_field_forward_train(long long n, const float* positions, c
 // Backward of the three MLPs (csrc/field_bwd_kernel.cuh).  weights_t: the blob of apnerf_field_forward with
 // every matrix transposed.  Outputs: g_* = activation gradients x loss_scale (fp16), d_enc fp32 unscaled.
 APNERF_API int apnerf_field_backward(long long n, const float* d_dens, const float* d_rgb, const float* d_sem,
-                                     int n_sem, const void* h1, const void* h2, const void* hh1, const void* hh2,
-                                     const void* hs1, const void* hs2, const void* weights_t, float loss_scale,
-                                     void* g_hh2, void* g_hs2, void* g_hh1, void* g_hs1, void* g_base, void* g_h2,
-                                     void* g_h1, float* d_enc, void* stream) {
+                                     int n_sem, long long act_stride, const void* h1, const void* h2,
+                                     const void* hh1, const void* hh2, const void* hs1, const void* hs2,
+                                     const void* weights_t, float loss_scale, long long g_stride, void* g_out_h,
+                                     void* g_out_s, void* g_hh2, void* g_hs2, void* g_hh1, void* g_hs1, void* g_base,
+                                     void* g_h2, void* g_h1, float* d_enc, void* stream) {
   if (n == 0) return 0;
   APNERF_REQUIRE(d_dens && d_rgb && h1 && h2 && hh1 && hh2 && hs1 && hs2 && weights_t, "field_backward: null input");
-  APNERF_REQUIRE(g_hh2 && g_hs2 && g_hh1 && g_hs1 && g_base && g_h2 && g_h1 && d_enc, "field_backward: null output");
+  APNERF_REQUIRE(g_out_h && g_out_s && g_hh2 && g_hs2 && g_hh1 && g_hs1 && g_base && g_h2 && g_h1 && d_enc,
+                 "field_backward: null output");
+  APNERF_REQUIRE(act_stride >= 128 && act_stride % 8 == 0 && g_stride >= 128 && g_stride % 8 == 0,
+                 "field_backward: row strides must be multiples of 8, >= 128");
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT && loss_scale > 0.f, "field_backward: bad n_sem / loss_scale");
   static bool attr_set = false;
   if (!attr_set) {
@@ -240,7 +247,8 @@ APNERF_API int apnerf_field_backward(long long n, const float* d_dens, const flo
   io.n = n, io.d_dens = d_dens, io.d_rgb = d_rgb, io.d_sem = d_sem, io.n_sem = d_sem ? n_sem : 0;
   io.h1 = (const __half*)h1, io.h2 = (const __half*)h2, io.hh1 = (const __half*)hh1, io.hh2 = (const __half*)hh2;
   io.hs1 = (const __half*)hs1, io.hs2 = (const __half*)hs2, io.weights_t = (const uint4*)weights_t;
-  io.loss_scale = loss_scale;
+  io.loss_scale = loss_scale, io.act_stride = act_stride, io.g_stride = g_stride;
+  io.g_out_h = (__half*)g_out_h, io.g_out_s = (__half*)g_out_s;
   io.g_hh2 = (__half*)g_hh2, io.g_hs2 = (__half*)g_hs2, io.g_hh1 = (__half*)g_hh1, io.g_hs1 = (__half*)g_hs1;
   io.g_base = (__half*)g_base, io.g_h2 = (__half*)g_h2, io.g_h1 = (__half*)g_h1, io.d_enc = d_enc;
   const long long tiles = (n + TILE_M - 1) / TILE_M;

@@ -37,7 +37,8 @@ struct FieldBwdIO {
   const float* d_rgb;    // [n, 3]   rgb logits
   const float* d_sem;    // [n, n_sem] semantic logits (may be nullptr)
   int n_sem;
-  // forward activations saved by the forward kernel (fp16, row-major)
+  // forward activations saved by the forward kernel (fp16, rows `act_stride` elements apart)
+  long long act_stride;
   const __half* h1;      // [n, 128]
   const __half* h2;      // [n, 128]
   const __half* hh1;     // [n, 64]
@@ -46,7 +47,11 @@ struct FieldBwdIO {
   const __half* hs2;     // [n, 64]
   const uint4* weights_t;  // transposed blob
   float loss_scale;
-  // outputs: activation gradients x loss_scale in fp16 (inputs of the weight-gradient GEMMs) ...
+  // outputs: activation gradients x loss_scale in fp16 (inputs of the weight-gradient GEMMs; rows `g_stride`
+  // elements apart) ...
+  long long g_stride;
+  __half* g_out_h;       // [n, 16]  incoming rgb-logit gradient, padded
+  __half* g_out_s;       // [n, 32]  incoming semantic-logit gradient, padded
   __half* g_hh2;         // [n, 64]
   __half* g_hs2;         // [n, 64]
   __half* g_hh1;         // [n, 64]
@@ -181,19 +186,24 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) field_backward_kernel(const Fi
         }
         const uint4* q = reinterpret_cast<const uint4*>(g);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(act + j * (TILE_M * 16) + row * 16) = q[j];
+        for (int j = 0; j < 2; ++j) {
+          *reinterpret_cast<uint4*>(act + j * (TILE_M * 16) + row * 16) = q[j];
+          if (valid) reinterpret_cast<uint4*>(io.g_out_h + s * io.g_stride)[j] = q[j];
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 4; ++j) {
           *reinterpret_cast<uint4*>(act + TILE_M * HEAD_OUT * 2 + j * (TILE_M * 16) + row * 16) = q[2 + j];
+          if (valid) reinterpret_cast<uint4*>(io.g_out_s + s * io.g_stride)[j] = q[2 + j];
+        }
       }
       rows_ready();
       // ---- hidden layers 2 and 1 of the head / semantic networks
 #pragma unroll 1
       for (int layer = 2; layer >= 1; --layer) {
-        const __half* ah = valid ? (layer == 2 ? io.hh2 : io.hh1) + s * HID2 : nullptr;
-        const __half* as = valid ? (layer == 2 ? io.hs2 : io.hs1) + s * HID2 : nullptr;
-        __half* gh = valid ? (layer == 2 ? io.g_hh2 : io.g_hh1) + s * HID2 : nullptr;
-        __half* gs = valid ? (layer == 2 ? io.g_hs2 : io.g_hs1) + s * HID2 : nullptr;
+        const __half* ah = valid ? (layer == 2 ? io.hh2 : io.hh1) + s * io.act_stride : nullptr;
+        const __half* as = valid ? (layer == 2 ? io.hs2 : io.hs1) + s * io.act_stride : nullptr;
+        __half* gh = valid ? (layer == 2 ? io.g_hh2 : io.g_hh1) + s * io.g_stride : nullptr;
+        __half* gs = valid ? (layer == 2 ? io.g_hs2 : io.g_hs1) + s * io.g_stride : nullptr;
         wait_mma();
         // invalid rows: mask pointer nullptr would pass the values through; their inputs were zero, so they stay zero
         mask_store_32(trow + 0, act, row, 0, ah, gh);
@@ -217,15 +227,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) field_backward_kernel(const Fi
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           *reinterpret_cast<uint4*>(act + j * (TILE_M * 16) + row * 16) = q[j];
-          if (valid) *reinterpret_cast<uint4*>(io.g_base + s * BASE_OUT + 8 * j) = q[j];
+          if (valid) *reinterpret_cast<uint4*>(io.g_base + s * io.g_stride + 8 * j) = q[j];
         }
       }
       rows_ready();
       // ---- base hidden layers 2 and 1
 #pragma unroll 1
       for (int layer = 2; layer >= 1; --layer) {
-        const __half* a = valid ? (layer == 2 ? io.h2 : io.h1) + s * HID : nullptr;
-        __half* g = valid ? (layer == 2 ? io.g_h2 : io.g_h1) + s * HID : nullptr;
+        const __half* a = valid ? (layer == 2 ? io.h2 : io.h1) + s * io.act_stride : nullptr;
+        __half* g = valid ? (layer == 2 ? io.g_h2 : io.g_h1) + s * io.g_stride : nullptr;
         wait_mma();
 #pragma unroll 1
         for (int c = 0; c < HID; c += 32) mask_store_32(trow + 0, act, row, c, a, g);

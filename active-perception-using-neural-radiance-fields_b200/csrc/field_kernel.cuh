@@ -103,6 +103,8 @@ struct FieldIO {
   int probabilistic;            // accumulate the variance terms
   // --- training forward (kernel instantiation TRAIN): density / rgb get the raw fp16 logits (no exp / sigmoid /
   // selector) and the activations the backward kernel needs are saved (fp16, row-major) ---
+  long long save_stride;        // elements between consecutive rows of every save_* matrix (they may be column
+                                // slices of one [n, 624] matrix, which makes the weight gradients ONE library GEMM)
   __half* save_enc;             // [n, 64]
   __half* save_h1;              // [n, 128]
   __half* save_h2;              // [n, 128]
@@ -394,7 +396,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       for (int j = 0; j < LEVELS_PER_ENC_THREAD / 2; ++j) {
         *reinterpret_cast<uint4*>(a0 + (part * (LEVELS_PER_ENC_THREAD / 2) + j) * (TILE_M * 16) + row * 16) = q[j];
         if (TRAIN && s < n)
-          reinterpret_cast<uint4*>(io.save_enc + s * ENC_DIM)[part * (LEVELS_PER_ENC_THREAD / 2) + j] = q[j];
+          reinterpret_cast<uint4*>(io.save_enc + s * io.save_stride)[part * (LEVELS_PER_ENC_THREAD / 2) + j] = q[j];
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar_full + 8 * buf);
@@ -476,7 +478,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         ptx::mbar_wait(my_mma, mma_ph), mma_ph ^= 1;
         ptx::tc_fence_after();
         {
-          __half* save = (TRAIN && s < n) ? (layer == 0 ? io.save_h1 : io.save_h2) + s * HID : nullptr;
+          __half* save = (TRAIN && s < n) ? (layer == 0 ? io.save_h1 : io.save_h2) + s * io.save_stride : nullptr;
 #pragma unroll 1
           for (int c = 0; c < HID; c += 32) relu_store_32(trow + TM_MAIN, act, row, c, save);
         }
@@ -538,9 +540,9 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(act + ACT_XS + j * (TILE_M * 16) + row * 16) = hq[2 + j];
         if (TRAIN && s < n) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(io.save_xh + s * HEAD_IN)[j] = hq[j];
+          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(io.save_xh + s * io.save_stride)[j] = hq[j];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) reinterpret_cast<uint4*>(io.save_xs + s * SEM_IN)[j] = hq[2 + j];
+          for (int j = 0; j < 2; ++j) reinterpret_cast<uint4*>(io.save_xs + s * io.save_stride)[j] = hq[2 + j];
         }
       }
       ptx::fence_proxy_async_smem();
@@ -551,8 +553,8 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       for (int layer = 0; layer < 2; ++layer) {
         ptx::mbar_wait(my_mma, mma_ph), mma_ph ^= 1;
         ptx::tc_fence_after();
-        __half* save_h = (TRAIN && s < n) ? (layer == 0 ? io.save_hh1 : io.save_hh2) + s * HID2 : nullptr;
-        __half* save_s = (TRAIN && s < n) ? (layer == 0 ? io.save_hs1 : io.save_hs2) + s * HID2 : nullptr;
+        __half* save_h = (TRAIN && s < n) ? (layer == 0 ? io.save_hh1 : io.save_hh2) + s * io.save_stride : nullptr;
+        __half* save_s = (TRAIN && s < n) ? (layer == 0 ? io.save_hs1 : io.save_hs2) + s * io.save_stride : nullptr;
         relu_store_32(trow + TM_H, act + ACT_HH, row, 0, save_h);
         relu_store_32(trow + TM_H, act + ACT_HH, row, 32, save_h);
         relu_store_32(trow + TM_S, act + ACT_HS, row, 0, save_s);

@@ -118,6 +118,42 @@ class _HashGridEncode(torch.autograd.Function):
 
 
 LOSS_SCALE = 128.0  # tcnn's default loss scale for fp16 networks (SURVEY.md Appendix C)
+# The weight-gradient GEMMs reduce over the samples in chunks of this many rows (buffers are padded with zero
+# rows): the library then only ever sees [chunks, out, CHUNK] x [chunks, CHUNK, in] problems.  With the raw
+# sample count as the GEMM's K every training step is a new problem shape, and planning one costs ~30 ms.
+WGRAD_CHUNK = 32768
+
+
+def _padded_rows(n: int) -> int:
+    return max(1, (n + WGRAD_CHUNK - 1) // WGRAD_CHUNK) * WGRAD_CHUNK
+
+
+def _rows(n: int, width: int, device, dtype=torch.float16) -> torch.Tensor:
+    """[padded n, width] buffer whose rows >= n are zero (the kernels write rows < n)."""
+    t = torch.empty((_padded_rows(n), width), device=device, dtype=dtype)
+    t[n:].zero_()
+    return t
+
+
+# Column layout of the two wide fp16 matrices of the training path.  X holds the forward activations the
+# backward needs (written by apnerf_field_forward_train), G the gradients w.r.t. every layer's output x LOSS_SCALE
+# (written by apnerf_field_backward).  Keeping them as column slices of one matrix each makes ALL weight
+# gradients one library GEMM  G^T . X  [576 x 624]; the nine diagonal blocks listed in _WGRAD_BLOCKS are dW.
+_X_COLS = dict(enc=(0, 64), h1=(64, 192), h2=(192, 320), xh=(320, 352), xs=(352, 368), hh1=(368, 432), hh2=(432, 496),
+               hs1=(496, 560), hs2=(560, 624))
+_G_COLS = dict(g_h1=(0, 128), g_h2=(128, 256), g_base=(256, 272), g_hh1=(272, 336), g_hh2=(336, 400),
+               g_out_h=(400, 416), g_hs1=(416, 480), g_hs2=(480, 544), g_out_s=(544, 576))
+_X_WIDTH, _G_WIDTH = 624, 576
+# (gradient block, activation block) in the order of the flat parameter vectors [W1|W2|W3], [WH1|WH2|WH3], [WS1|WS2|WS3]
+_WGRAD_BLOCKS = (("g_h1", "enc"), ("g_h2", "h1"), ("g_base", "h2"), ("g_hh1", "xh"), ("g_hh2", "hh1"), ("g_out_h", "hh2"),
+                 ("g_hs1", "xs"), ("g_hs2", "hs1"), ("g_out_s", "hs2"))
+
+
+def _cols(mat: torch.Tensor, layout: dict, name: str):
+    """Device pointer of a column block of a wide row-major fp16 matrix (the kernels take the row stride)."""
+    import ctypes
+
+    return ctypes.c_void_p(mat.data_ptr() + 2 * layout[name][0])
 
 
 class _FusedMLPs(torch.autograd.Function):
@@ -127,8 +163,8 @@ class _FusedMLPs(torch.autograd.Function):
               network outputs and to save every layer's activation;
     backward  ``apnerf_field_backward`` (tcgen05 chain of dX = dY . W with the ReLU masks, gradients x LOSS_SCALE
               in fp16 like tcnn) + ``apnerf_hashgrid_encode_bwd`` (scatter-add into the fp32 table gradient);
-              the weight gradients dW = dY^T . X are nine plain library GEMMs over all samples with fp32
-              accumulation, as tcnn computes them with CUTLASS.
+              the weight gradients dW = dY^T . X are one plain library GEMM over all samples (fp16 operands,
+              fp32 accumulation and output), as tcnn computes them with CUTLASS.
 
     Inputs: positions, directions [n, 3] f32 and the three flat fp32 parameter vectors.  Outputs: density
     logit [n], rgb logits [n, 3], semantic logits [n, C] (fp16 values upcast)."""
@@ -141,8 +177,7 @@ class _FusedMLPs(torch.autograd.Function):
         dev = pos.device
         C = field.num_semantic_classes
         weights, table = field._packed()
-        f16 = dict(device=dev, dtype=torch.float16)
-        saves = [torch.empty((n, w), **f16) for w in (64, 128, 128, 32, 16, 64, 64, 64, 64)]
+        X = _rows(n, _X_WIDTH, dev)
         dens = torch.empty(n, device=dev, dtype=torch.float32)
         rgb = torch.empty((n, 3), device=dev, dtype=torch.float32)
         sem = torch.empty((n, C), device=dev, dtype=torch.float32) if C > 0 else None
@@ -151,9 +186,9 @@ class _FusedMLPs(torch.autograd.Function):
             with torch.cuda.device(dev):
                 call("apnerf_field_forward_train", n, pos, dirs, aabb_host.ctypes.data_as(ctypes.c_void_p),
                      field.n_levels, field._meta.ctypes.data_as(ctypes.c_void_p), table, weights, dens, rgb, sem, C,
-                     *saves)
+                     _X_WIDTH, *[_cols(X, _X_COLS, k) for k in ("enc", "h1", "h2", "xh", "xs", "hh1", "hh2", "hs1", "hs2")])
         ctx.field = field
-        ctx.save_for_backward(pos, *saves)
+        ctx.save_for_backward(pos, X)
         if C > 0:
             return dens, rgb, sem
         return dens, rgb
@@ -163,7 +198,7 @@ class _FusedMLPs(torch.autograd.Function):
         import ctypes
 
         field = ctx.field
-        pos, enc, h1, h2, xh, xs, hh1, hh2, hs1, hs2 = ctx.saved_tensors
+        pos, X = ctx.saved_tensors
         n = pos.shape[0]
         dev = pos.device
         C = field.num_semantic_classes
@@ -173,39 +208,31 @@ class _FusedMLPs(torch.autograd.Function):
             g_sem = (torch.zeros((n, C), device=dev) if g_sem is None else g_sem.float()).contiguous()
         else:
             g_sem = None
-        f16 = dict(device=dev, dtype=torch.float16)
-        g_hh2, g_hs2, g_hh1, g_hs1 = (torch.empty((n, 64), **f16) for _ in range(4))
-        g_base = torch.empty((n, 16), **f16)
-        g_h2, g_h1 = torch.empty((n, 128), **f16), torch.empty((n, 128), **f16)
+        G = _rows(n, _G_WIDTH, dev)
         d_enc = torch.empty((n, 64), device=dev, dtype=torch.float32)
-        d_table = torch.zeros((field._n_entries, 4), device=dev, dtype=torch.float32)
+        # the flat gradient of mlp_base.params = [W1 | W2 | W3 | table]: the scatter kernel adds straight into its tail
+        base_grad = torch.zeros(field._n_base_w + field._n_entries * 4, device=dev, dtype=torch.float32)
+        d_table = base_grad[field._n_base_w:]
         if n:
             aabb_min, aabb_max = torch.split(field.aabb, 3, dim=-1)
             x01 = ((pos - aabb_min) / (aabb_max - aabb_min)).contiguous()
             with torch.cuda.device(dev):
-                call("apnerf_field_backward", n, g_dens, g_rgb, g_sem, C, h1, h2, hh1, hh2, hs1, hs2,
-                     field._packed_t(), float(LOSS_SCALE), g_hh2, g_hs2, g_hh1, g_hs1, g_base, g_h2, g_h1, d_enc)
+                call("apnerf_field_backward", n, g_dens, g_rgb, g_sem, C, _X_WIDTH,
+                     *[_cols(X, _X_COLS, k) for k in ("h1", "h2", "hh1", "hh2", "hs1", "hs2")],
+                     field._packed_t(), float(LOSS_SCALE), _G_WIDTH,
+                     *[_cols(G, _G_COLS, k) for k in ("g_out_h", "g_out_s", "g_hh2", "g_hs2", "g_hh1", "g_hs1", "g_base",
+                                                      "g_h2", "g_h1")], d_enc)
                 call("apnerf_hashgrid_encode_bwd", n, x01, field.n_levels,
                      field._meta.ctypes.data_as(ctypes.c_void_p),
                      d_enc[:, : field.n_levels * 4].contiguous(), d_table)
-
-        def wgrad(g, x, scaled=True):  # dW [out, in] = g^T . x over all samples, fp32 accumulation
-            w = g.float().t() @ x.float()
-            return w / LOSS_SCALE if scaled else w
-
-        def padded(g, rows):  # gradients of the zero-padded output rows are zero
-            out = torch.zeros((rows, g.shape[1]), device=dev, dtype=torch.float32)
-            out[: g.shape[0]] = g
-            return out
-
-        base_grad = torch.cat([wgrad(g_h1, enc).reshape(-1), wgrad(g_h2, h1).reshape(-1),
-                               wgrad(g_base, h2).reshape(-1), d_table.reshape(-1)])
-        head_grad = torch.cat([wgrad(g_hh1, xh).reshape(-1), wgrad(g_hh2, hh1).reshape(-1),
-                               padded(wgrad(g_rgb, hh2, scaled=False), 16).reshape(-1)])
-        sem_grad = None
-        if C > 0:
-            sem_grad = torch.cat([wgrad(g_hs1, xs).reshape(-1), wgrad(g_hs2, hs1).reshape(-1),
-                                  padded(wgrad(g_sem, hs2, scaled=False), 32).reshape(-1)])
+        # all weight gradients: G^T . X reduced over the samples in fixed-size chunks (see WGRAD_CHUNK)
+        chunks = X.shape[0] // WGRAD_CHUNK
+        GX = torch.bmm(G.view(chunks, WGRAD_CHUNK, _G_WIDTH).transpose(1, 2), X.view(chunks, WGRAD_CHUNK, _X_WIDTH),
+                       out_dtype=torch.float32).sum(0) / LOSS_SCALE
+        dW = [GX[_G_COLS[g][0]:_G_COLS[g][1], _X_COLS[x][0]:_X_COLS[x][1]].reshape(-1) for g, x in _WGRAD_BLOCKS]
+        base_grad[: field._n_base_w] = torch.cat(dW[0:3])
+        head_grad = torch.cat(dW[3:6])
+        sem_grad = torch.cat(dW[6:9]) if C > 0 else None
         return None, None, base_grad, head_grad, sem_grad, None
 
 

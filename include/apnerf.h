@@ -133,25 +133,29 @@ int apnerf_field_weight_bytes(void);
  *   apnerf_field_forward_train: the kernel of apnerf_field_forward with RAW outputs (fp16 network outputs upcast:
  *       density logit [n], rgb logits [n,3], semantic logits [n,n_sem]) and the activations the backward
  *       needs saved as row-major fp16: enc [n,64], h1 [n,128], h2 [n,128], xh [n,32] (16 SH | 15 geo | 1.0),
- *       xs [n,16] (15 geo | 1.0), hh1, hh2, hs1, hs2 [n,64].
+ *       xs [n,16] (15 geo | 1.0), hh1, hh2, hs1, hs2 [n,64]; rows are save_stride fp16 elements apart, so the
+ *       nine matrices can be column slices of one [n, 624] matrix (then all weight gradients are ONE GEMM).
  *   apnerf_field_backward: d_dens [n], d_rgb [n,3], d_sem [n,n_sem] (fp32, NULL ok) -> the chain of dX = dY.W
  *       products on the tensor cores (csrc/field_bwd_kernel.cuh): g_* = gradients w.r.t. every layer's
- *       pre-activation output x loss_scale in fp16 (g_base [n,16] for the base output), d_enc [n,64] fp32
+ *       pre-activation output x loss_scale in fp16 (g_base [n,16] for the base output; g_out_h [n,16] /
+ *       g_out_s [n,32] are the padded incoming gradients; rows g_stride elements apart), d_enc [n,64] fp32
  *       unscaled (feeds apnerf_hashgrid_encode_bwd).  weights_t: the blob of apnerf_field_forward with every
  *       matrix transposed ([in,out] in the same UMMA layout, same offsets).  Weight gradients are the plain
  *       GEMMs dW = g^T . x the caller runs with a library (as tcnn does). */
 int apnerf_field_forward_train(long long n, const float* positions, const float* directions,
                                const float* aabb_host, int n_levels, const uint32_t* meta_host,
                                const void* table, const void* weights, float* dens_logit,
-                               float* rgb_logit, float* sem_logit, int n_sem, void* save_enc,
+                               float* rgb_logit, float* sem_logit, int n_sem, long long save_stride,
+                               void* save_enc,
                                void* save_h1, void* save_h2, void* save_xh, void* save_xs,
                                void* save_hh1, void* save_hh2, void* save_hs1, void* save_hs2,
                                void* stream);
 int apnerf_field_backward(long long n, const float* d_dens, const float* d_rgb, const float* d_sem,
-                          int n_sem, const void* h1, const void* h2, const void* hh1, const void* hh2,
-                          const void* hs1, const void* hs2, const void* weights_t, float loss_scale,
-                          void* g_hh2, void* g_hs2, void* g_hh1, void* g_hs1, void* g_base, void* g_h2,
-                          void* g_h1, float* d_enc, void* stream);
+                          int n_sem, long long act_stride, const void* h1, const void* h2,
+                          const void* hh1, const void* hh2, const void* hs1, const void* hs2,
+                          const void* weights_t, float loss_scale, long long g_stride, void* g_out_h,
+                          void* g_out_s, void* g_hh2, void* g_hs2, void* g_hh1, void* g_hs1, void* g_base,
+                          void* g_h2, void* g_h1, float* d_enc, void* stream);
 
 /* OccGridEstimator._update -- perception/nerfacc/nerfacc/estimators/occ_grid.py:377-437, the per-level body
  * fused into the field kernel: x = level_aabb_lo + ((grid_coords(cell) + jitter) / res) * extent; occ =

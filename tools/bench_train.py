@@ -25,7 +25,7 @@ est.occs = est.binaries.flatten().float() * 0.5
 est = est.to(dev)
 f = apnerf.NGPRadianceField(synthetic.ROI_AABB, layers=2, num_semantic_classes=29)
 f = synthetic.init_trained_like(f, seed=2, density_gain=2.0).to(dev)
-opt = torch.optim.Adam(f.parameters(), lr=1e-3, eps=1e-15)
+opt = torch.optim.Adam(f.parameters(), lr=1e-3, eps=1e-15)  # pipeline.py:173-178
 g = torch.Generator().manual_seed(4 + rank)
 d = torch.randn((N_RAYS, 3), generator=g)
 d = d / d.norm(dim=-1, keepdim=True)
