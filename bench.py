@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 W, H, HFOV_FOCAL = 320, 240, 160.0
 OPTS = dict(near_plane=0.1, render_step_size=1e-3, cone_angle=0.004, alpha_thre=0.01)
 METRIC = "rays/s rendered+scored (pred-info)"
-NCU_DRAM_BYTES_PER_SAMPLE = 73.6  # profiles/r01_field_kernel.md (dram__bytes_read.sum + write.sum per sample)
+NCU_DRAM_BYTES_PER_SAMPLE = 104.4  # profiles/r01_field_kernel.md (dram__bytes_read.sum + write.sum per sample)
 N_SEM = 29
 
 
@@ -327,7 +327,7 @@ def field_kernel_roofline(torch, scorer, c2w, vt, n_traj):
             "achieved": achieved, "peak": peak, "peak_kind": peak_kind + " HBM copy GB/s (MEASURED_PEAKS.json)",
             "unit": "GB/s", "frac": achieved / peak,
             # DRAM bytes per launch from the ncu --set full capture of this kernel (profiles/r01_field_kernel.md:
-            # 73.6 B of dram read+write per sample -- the 48 MB table is L2-resident) x samples per launch
+            # 104 B of dram read+write per sample -- the 48 MB table is L2-resident) x samples per launch
             "traffic": NCU_DRAM_BYTES_PER_SAMPLE * n_samples / max(1, n_launch),
             "algorithmic_bytes_per_launch": bytes_per_sample * n_samples / max(1, n_launch),
             "algorithmic_bytes_per_sample": bytes_per_sample, "samples_per_step": n_samples,
