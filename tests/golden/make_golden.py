@@ -301,7 +301,13 @@ def main_sampling():
         for name, v in zip(("rgb", "opacity", "depth"), g[:3]):
             out[f"test_{name}"] = v.numpy()
         out["test_n"] = np.int64(g[3])
-    print("wrappers: samples", int(out["guide_n"]), int(out["occgrid_n"]), int(out["test_n"]))
+        # two grid levels (sorted interval ends, grid.py:158-162 / utils.py:884-890) through the probabilistic renderer
+        g = utils.render_probablistic_image_with_occgrid_test(256, field, e2, rays, near_plane=0.2, render_step_size=1e-2,
+                                                              cone_angle=0.004, alpha_thre=0.01, render_bkgd=bk)
+        for name, v in zip(("rgb", "rgb_var", "opacity", "depth", "depth_var", "sem"), g[:6]):
+            out[f"lvl2_{name}"] = v.numpy()
+        out["lvl2_n"] = np.int64(g[6])
+    print("wrappers: samples", int(out["guide_n"]), int(out["occgrid_n"]), int(out["test_n"]), int(out["lvl2_n"]))
 
     # ---- S4: OccGridEstimator._update, warm-up branch (all cells), jitter patched to the cell centre
     res = 32

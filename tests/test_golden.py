@@ -272,6 +272,12 @@ def test_cuda_render_wrappers_match_reference_python(apnerf, gold):
         check("occgrid", apnerf.render_image_with_occgrid(plain, e1, rays, test_chunk_size=300, **opts),
               ("rgb", "opacity", "depth"))
         check("test", apnerf.render_image_with_occgrid_test(1024, plain, e1, rays, **opts), ("rgb", "opacity", "depth"))
+        # two occupancy-grid levels: the drop-in routes to the op-by-op CUDA path (sorted interval ends)
+        e2 = _ops_estimator(apnerf, cfg, 2, 4, dev)
+        check("lvl2", apnerf.render_probablistic_image_with_occgrid_test(
+            256, field(cfg["field_seeds"][0], cfg["n_classes"]), e2, rays, near_plane=0.2, render_step_size=1e-2,
+            cone_angle=0.004, alpha_thre=0.01, render_bkgd=opts["render_bkgd"]),
+            ("rgb", "rgb_var", "opacity", "depth", "depth_var", "sem"))
 
 
 @pytest.mark.gpu
