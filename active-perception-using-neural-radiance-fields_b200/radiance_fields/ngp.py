@@ -166,11 +166,11 @@ class _FusedMLPs(torch.autograd.Function):
               the weight gradients dW = dY^T . X are one plain library GEMM over all samples (fp16 operands,
               fp32 accumulation and output), as tcnn computes them with CUTLASS.
 
-    Inputs: positions, directions [n, 3] f32 and the three flat fp32 parameter vectors.  Outputs: density
+    Inputs: positions, directions [n, 3] f32 and the flat fp32 parameter vectors (the SH one is empty).  Outputs: density
     logit [n], rgb logits [n, 3], semantic logits [n, C] (fp16 values upcast)."""
 
     @staticmethod
-    def forward(ctx, pos, dirs, base_params, head_params, sem_params, field):
+    def forward(ctx, pos, dirs, base_params, head_params, sem_params, dir_params, field):
         import ctypes
 
         n = pos.shape[0]
@@ -233,7 +233,10 @@ class _FusedMLPs(torch.autograd.Function):
         base_grad[: field._n_base_w] = torch.cat(dW[0:3])
         head_grad = torch.cat(dW[3:6])
         sem_grad = torch.cat(dW[6:9]) if C > 0 else None
-        return None, None, base_grad, head_grad, sem_grad, None
+        # the zero-length SH parameter vector gets a (zero-length) gradient too: the reference's NaN guard calls
+        # torch.isnan(param.grad) on EVERY named parameter (scripts/pipeline.py:521-524)
+        dir_grad = torch.zeros(0, device=dev, dtype=torch.float32)
+        return None, None, base_grad, head_grad, sem_grad, dir_grad, None
 
 
 class NGPRadianceField(torch.nn.Module):
@@ -415,7 +418,8 @@ class NGPRadianceField(torch.nn.Module):
         x = (pos - aabb_min) / (aabb_max - aabb_min)
         selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
         sem_params = self.mlp_sem.params if self.num_semantic_classes > 0 else None
-        out = _FusedMLPs.apply(pos, dirs, self.mlp_base.params, self.mlp_head.params, sem_params, self)
+        out = _FusedMLPs.apply(pos, dirs, self.mlp_base.params, self.mlp_head.params, sem_params,
+                               self.direction_encoding.params, self)
         density = self.density_activation(out[0][:, None]) * selector[:, None]
         if density_only:
             return density.reshape(-1), None, None, None

@@ -225,3 +225,41 @@ def test_fused_occupancy_update_matches_op_by_op(apnerf):
     assert 0.5 < once.float().mean().item() < 1.0
     assert torch.equal(a_occ[once], b_occ[once])
     assert (a_bin == b_bin).float().mean().item() >= 0.98
+
+
+def test_training_without_semantics_and_edge_inputs(apnerf):
+    """A field without a semantic head trains (the backward kernel runs with no semantic gradient), query_density is
+    differentiable, empty batches are accepted, and the saved-activation path reproduces the inference kernel exactly
+    for a number of points that is not a multiple of the 128-row tile."""
+    f = _field(apnerf, seed=5, C=0).train()
+    g = torch.Generator().manual_seed(2)
+    n = 1000  # not a multiple of 128
+    lo, hi = torch.tensor(AABB[:3]), torch.tensor(AABB[3:])
+    pos = (lo + (hi - lo) * torch.rand((n, 3), generator=g)).to(DEV)
+    pos[:7] = torch.tensor(AABB[3:]).to(DEV) + 1.0  # outside the aabb: the selector zeroes the density and its gradient
+    dirs = torch.randn((n, 3), generator=g)
+    dirs = (dirs / dirs.norm(dim=-1, keepdim=True)).to(DEV)
+    out = f(pos, dirs)
+    assert len(out) == 2
+    rgb, dens = out
+    assert float(dens[:7].detach().abs().max()) == 0.0
+    (rgb.square().mean() + dens.mean() * 1e-2).backward()
+    grads = {k: p.grad for k, p in f.named_parameters()}
+    assert set(grads) == {"direction_encoding.params", "mlp_base.params", "mlp_head.params"}
+    assert all(v is not None and torch.isfinite(v).all() for v in grads.values())
+    assert float(grads["mlp_base.params"].abs().sum()) > 0 and float(grads["mlp_head.params"].abs().sum()) > 0
+    f.eval()
+    with torch.no_grad():
+        rgb0, dens0 = f(pos, dirs)
+    assert torch.equal(rgb0, rgb.detach()) and torch.equal(dens0, dens.detach())  # same kernel, same rounding points
+    # differentiable query_density
+    f.train()
+    f.zero_grad()
+    d2 = f.query_density(pos)
+    assert d2.shape == (n, 1) and d2.requires_grad
+    d2.sum().backward()
+    assert float(f.mlp_base.params.grad.abs().sum()) > 0
+    # empty input
+    e = f(pos[:0], dirs[:0])
+    assert e[0].shape == (0, 3) and e[1].shape == (0, 1)
+    (e[0].sum() + e[1].sum()).backward()
