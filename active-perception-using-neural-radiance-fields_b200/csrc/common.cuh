@@ -65,7 +65,7 @@ static inline float apnerf_skip_min_steps() {
   static float v = -1.f;
   if (v < 0.f) {
     const char* e = getenv("APNERF_SKIP_MIN");
-    v = e ? (float)atof(e) : 32.f;
+    v = e ? (float)atof(e) : 256.f;
   }
   return v;
 }

@@ -97,3 +97,21 @@ def test_field_rejects_unsupported_configs_loudly(apnerf):
     f = apnerf.NGPRadianceField([-1, -1, -1, 1, 1, 1], layers=2, num_semantic_classes=3)
     with pytest.raises(RuntimeError):
         f.query_density(torch.zeros(4, 3))  # CPU tensors: no fallback
+
+
+def test_closed_form_skip_is_bit_exact_when_forced():
+    """The exact closed-form empty-space skip (csrc/march.cuh: skip_to) is only taken for skips of more than
+    APNERF_SKIP_MIN = 256 steps by default, which the ordinary fixtures rarely reach.  Re-run the bit-exact
+    comparisons against the reference's own kernels and the oracle in a child process that forces it for every
+    skip longer than two steps (the knob is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, APNERF_SKIP_MIN="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        os.path.join(root, "tests", "test_gpu_reference.py"),
+                        os.path.join(root, "tests", "test_render_gpu.py") + "::test_schedule_and_samples_bit_exact"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
