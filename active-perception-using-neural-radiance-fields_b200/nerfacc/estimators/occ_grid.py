@@ -154,7 +154,7 @@ class OccGridEstimator(torch.nn.Module):
 
         f = occ_eval_fn.radiance_field
         weights, table = f._packed()
-        aabb_host = np.asarray(f.aabb.detach().cpu().numpy(), dtype=np.float32)
+        aabb_host = f.aabb_host()
         lvl_aabb = np.ascontiguousarray(self.aabbs[lvl].detach().cpu().numpy(), dtype=np.float32)
         res = [int(v) for v in self.resolution.tolist()]
         lo, hi = lvl * self.cells_per_lvl, (lvl + 1) * self.cells_per_lvl

@@ -181,7 +181,7 @@ class _FusedMLPs(torch.autograd.Function):
         dens = torch.empty(n, device=dev, dtype=torch.float32)
         rgb = torch.empty((n, 3), device=dev, dtype=torch.float32)
         sem = torch.empty((n, C), device=dev, dtype=torch.float32) if C > 0 else None
-        aabb_host = np.asarray(field.aabb.detach().cpu().numpy(), dtype=np.float32)
+        aabb_host = field.aabb_host()
         if n:
             with torch.cuda.device(dev):
                 call("apnerf_field_forward_train", n, pos, dirs, aabb_host.ctypes.data_as(ctypes.c_void_p),
@@ -339,6 +339,16 @@ class NGPRadianceField(torch.nn.Module):
             self._cache_key = key
         return self._cache
 
+    def aabb_host(self) -> np.ndarray:
+        """The aabb as a host float32[6] array for the C-ABI calls, read back from the device once (the buffer is
+        normally constant; the copy is keyed on the buffer's storage and version counter, so ``load_state_dict`` or a
+        move to another device refresh it)."""
+        key = (self.aabb.data_ptr(), self.aabb._version, str(self.aabb.device))
+        if getattr(self, "_aabb_host", None) is None or getattr(self, "_aabb_host_key", None) != key:
+            self._aabb_host = np.ascontiguousarray(self.aabb.detach().cpu().numpy(), dtype=np.float32)
+            self._aabb_host_key = key
+        return self._aabb_host
+
     def _packed_t(self):
         """The weight blob of ``_packed`` with every matrix transposed ([in, out], same UMMA layout and
         offsets): the B operands of the backward kernel's dX = dY . W products."""
@@ -375,9 +385,7 @@ class NGPRadianceField(torch.nn.Module):
         n = pos.shape[0]
         dev = pos.device
         density = torch.empty(n, device=dev, dtype=torch.float32)
-        aabb_host = (np.asarray(self.aabb.detach().cpu().numpy(), dtype=np.float32)
-                     if getattr(self, "_aabb_host", None) is None else self._aabb_host)
-        self._aabb_host = aabb_host
+        aabb_host = self.aabb_host()
         feat = torch.empty((n, 15), device=dev, dtype=torch.float16) if return_feat else None
         rgb = sem = dirs = None
         C = self.num_semantic_classes

@@ -139,7 +139,7 @@ class FusedRenderer:
         aabbs = estimator.aabbs.contiguous().float()
         rx, ry, rz = (int(v) for v in binaries.shape[1:])
         weights, table = radiance_field._packed()
-        aabb_host = np.asarray(radiance_field.aabb.detach().cpu().numpy(), dtype=np.float32)
+        aabb_host = radiance_field.aabb_host()
         meta = radiance_field._meta
         opc_thre = float(np.float32(1 - early_stop_eps))
         max_iters = (max_samples + min_samples - 1) // min_samples
