@@ -349,8 +349,9 @@ __global__ void __launch_bounds__(CMP_T) render_compact_kernel(const int* counte
 // (utils.py:957-999), next ray mask (utils.py:1004-1009) and compaction of the live list.
 // (A 4-lanes-per-ray variant was measured slower: the weights' exp() calls were then issued by every
 // lane and the kernel became MUFU-bound.)  The weights of the first pass are kept in a small per-thread
-// array and the 32 semantic accumulators are processed 16 at a time, which keeps the kernel at ~80
-// registers (6 CTAs of 128 threads per SM instead of 3): it is latency-bound on the scattered per-ray state.
+// array and the 32 semantic accumulators are processed 16 at a time, which lets the kernel run at 64
+// registers (8 CTAs of 128 threads per SM instead of 3 at 168): ncu shows it memory-latency bound (long
+// scoreboard 12 of 16 stall cycles per issue), so resident warps are what it needs; 48 registers measured slower.
 // Sample row (40 fp16): [density logit, r, g, b logits, sigma as fp32 (2 halves), 0, 0 | 32 sem logits].
 struct SampleTerms {
   float w, col[3], tmid;
@@ -374,7 +375,7 @@ __device__ __forceinline__ SampleTerms sample_terms(const uint4& r0, float t0, f
 }
 
 template <bool PROB>
-__global__ void __launch_bounds__(128, 6) render_composite_kernel(
+__global__ void __launch_bounds__(128, 8) render_composite_kernel(
     const int* counters_in, int n_rays, int rays_per_call, int n_sem,
     const int* __restrict__ alive, const int* __restrict__ entry_base, const int* __restrict__ entry_cnt,
     const float* __restrict__ s_ts, const float* __restrict__ s_te, const uint4* __restrict__ rows,
