@@ -62,3 +62,42 @@ def test_umma_weight_packing(apnerf):
     p = _umma_pack(w)
     for n, k in [(0, 0), (3, 5), (15, 31), (7, 8), (8, 17)]:
         assert p[(k // 8) * (16 * 8) + n * 8 + k % 8] == w[n, k]
+
+
+def test_training_matrix_layouts_are_consistent():
+    """Host-side bookkeeping of the training path: the column blocks of the two wide fp16 matrices tile them exactly,
+    every weight-gradient block pairs a gradient with the activation that produced it (shapes of the flat parameter
+    vectors), and row padding is a whole number of GEMM chunks."""
+    import apnerf
+    from apnerf.radiance_fields import ngp
+
+    for layout, width in ((ngp._X_COLS, ngp._X_WIDTH), (ngp._G_COLS, ngp._G_WIDTH)):
+        spans = sorted(layout.values())
+        assert spans[0][0] == 0 and spans[-1][1] == width
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert all(lo % 8 == 0 for lo, _ in spans)  # 16-byte aligned column blocks
+    f = apnerf.NGPRadianceField([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], layers=2, num_semantic_classes=29)
+    dims = f._base_dims + f._head_dims + f._sem_dims
+    assert len(dims) == len(ngp._WGRAD_BLOCKS) == 9
+    for (n_out, n_in), (g, x) in zip(dims, ngp._WGRAD_BLOCKS):
+        assert ngp._G_COLS[g][1] - ngp._G_COLS[g][0] == n_out, (g, n_out)
+        assert ngp._X_COLS[x][1] - ngp._X_COLS[x][0] == n_in, (x, n_in)
+    for n in (0, 1, ngp.WGRAD_CHUNK - 1, ngp.WGRAD_CHUNK, ngp.WGRAD_CHUNK + 1, 5 * ngp.WGRAD_CHUNK):
+        p = ngp._padded_rows(n)
+        assert p >= max(n, 1) and p % ngp.WGRAD_CHUNK == 0 and p - n < ngp.WGRAD_CHUNK + (n == 0)
+
+
+def test_view_selection_matches_reference_indexing_for_short_trajectories():
+    """pipeline.py:687-697 indexes trajectory[unc_idx] with numpy semantics: 40 indices with repeats, and negative
+    ones (trajectories shorter than 20 poses) wrap around.  The scorer must pick the same poses."""
+    import numpy as np
+
+    from apnerf.scoring import uncertainty_view_indices
+
+    for n in (10, 19, 20, 21, 24, 40, 41, 100):  # below 10 poses the reference itself raises IndexError
+        traj = np.arange(n * 7, dtype=np.float64).reshape(n, 7)
+        a = np.linspace(0, n - 20, 20)
+        b = np.linspace(n - 20, n - 1, 20)
+        ref = traj[np.hstack((a, b)).astype(int)]
+        got = traj[uncertainty_view_indices(n)]
+        assert got.shape == (40, 7) and np.array_equal(got, ref)
