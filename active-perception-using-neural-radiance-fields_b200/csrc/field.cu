@@ -172,7 +172,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   if (tiles < 1) tiles = 1;
   const int sms = apnerf_num_sms();
   const int grid = (int)(tiles < sms ? tiles : sms);
-  field_forward_kernel<false><<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  field_forward_kernel<false><<<grid, FIELD_THREADS, FIELD_SMEM_MIN, (cudaStream_t)stream>>>(io, m, fc);
   APNERF_CHECK_LAUNCH("field_forward_kernel");
   return 0;
 }
@@ -218,7 +218,7 @@ APNERF_API int apnerf_field_forward_train(long long n, const float* positions, c
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const long long tiles = (n + TILE_M - 1) / TILE_M;
   const int sms = apnerf_num_sms();
-  field_forward_kernel<true><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  field_forward_kernel<true><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM_MIN, (cudaStream_t)stream>>>(io, m, fc);
   APNERF_CHECK_LAUNCH("field_forward_kernel(train)");
   return 0;
 }
@@ -289,7 +289,7 @@ APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const f
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const long long tiles = (n + TILE_M - 1) / TILE_M;
   const int sms = apnerf_num_sms();
-  field_forward_kernel<false><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
+  field_forward_kernel<false><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM_MIN, (cudaStream_t)stream>>>(io, m, fc);
   APNERF_CHECK_LAUNCH("field_forward_kernel(occ_update)");
   return 0;
 }

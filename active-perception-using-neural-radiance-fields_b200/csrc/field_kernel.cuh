@@ -31,20 +31,17 @@ constexpr int N_ENC_THREADS = N_ENC_WARPS * 32;                                /
 constexpr int LEVELS_PER_ENC_THREAD = MAX_LEVELS * TILE_M / N_ENC_THREADS;     // 4
 constexpr int A0_STAGES = 2;
 
-// shared-memory map (bytes).  Per chain ONE 32 KB activation region is reused by every layer:
-//   H  [128 x 128] at +0                      (base layers 1, 2 outputs)
-//   XH [128 x 32]  at +0,  XS [128 x 16] at +8192    (head / semantic inputs; H is dead by then)
-//   HH [128 x 64]  at +0,  HS [128 x 64] at +16384   (head / semantic hidden; XH / XS are dead)
+// shared-memory map (bytes): all nine weight matrices, the encoders' A-tile ring, barriers = 112 KB, which leaves
+// 96 KB of the SM's unified array as L1 for the hash-grid gathers.  Activations between layers live in TMEM (below);
+// only the variant with the compositor fused into the epilogue adds a 32 KB scratch region per chain.
 constexpr int SM_W = 0;
 constexpr int SM_A0 = SM_W + W_BYTES;                             // A0_STAGES x [128 x 64] fp16
-constexpr int SM_ACT = SM_A0 + A0_STAGES * TILE_M * ENC_DIM * 2;  // N_CHAINS x 32 KB
+constexpr int SM_BAR = SM_A0 + A0_STAGES * TILE_M * ENC_DIM * 2;  // mbarriers + tmem base
+constexpr int SM_ACT = SM_BAR + 128;                              // N_CHAINS x 32 KB, fused compositor only
 constexpr int ACT_BYTES = TILE_M * HID * 2;
-constexpr int ACT_XH = 0, ACT_XS = TILE_M * HEAD_IN * 2, ACT_HH = 0, ACT_HS = TILE_M * HID2 * 2;
-constexpr int SM_BAR = SM_ACT + N_CHAINS * ACT_BYTES;             // mbarriers + tmem base
-constexpr int FIELD_SMEM = SM_BAR + 128;
-// Fused compositing scratch ALIASES the chain's activation region (dead once the last layer's MMA has
-// completed, until the next tile's first epilogue stage): keeping the footprint at 192 KB matters,
-// the rest of the 228 KB is the L1 cache the hash-grid gathers hit 50 % of the time.
+constexpr int FIELD_SMEM_MIN = SM_ACT;                            // 112 KB: weights + encode ring + barriers
+constexpr int FIELD_SMEM = SM_ACT + N_CHAINS * ACT_BYTES;         // + the fused compositor's per-chain scratch
+// Fused compositing scratch, one region per chain:
 constexpr int ROWBUF_BYTES = 5 * TILE_M * 16;                     // 5 chunks x [128 x 16 B] raw fp16 rows
 constexpr int ACT_ROWBUF = 0;
 constexpr int ACT_FBUF = ACT_ROWBUF + ROWBUF_BYTES;               // [6][128] f32 per-sample terms
@@ -53,15 +50,24 @@ constexpr int ACT_CBUF = ACT_WBUF + TILE_M * 4;                   // [128] u8 ro
 static_assert(ACT_CBUF + TILE_M <= ACT_BYTES, "compositing scratch must fit the activation region");
 static_assert(FIELD_SMEM <= 232448, "field kernel shared memory exceeds 227 KB");
 
-// TMEM column map per chain (fp32 accumulators, 128 lanes, 128 columns, reused layer by layer)
-constexpr uint32_t TM_CHAIN = 128;
+// TMEM column map per chain: fp32 accumulators (128 lanes x 128 columns, reused layer by layer) and, next to them,
+// the fp16 A operand of the NEXT layer (two halves per column): the epilogue hands activations to the tensor core
+// through TMEM (tcgen05.st -> tcgen05.mma with A from TMEM), not through shared memory, which takes the
+// activation stores off the L1 / shared-memory pipe that bounds this kernel.
+constexpr uint32_t TM_CHAIN = 256;
 constexpr uint32_t TM_MAIN = 0;   // 128 cols: base layer 1 / 2 outputs
 constexpr uint32_t TM_OUT3 = 0;   // 16 cols : base output (density, geo features)
 constexpr uint32_t TM_H = 0;      // 64 cols : head hidden
 constexpr uint32_t TM_S = 64;     // 64 cols : semantic hidden
 constexpr uint32_t TM_HO = 0;     // 16 cols : rgb (padded)
 constexpr uint32_t TM_SO = 16;    // 32 cols : semantic logits (padded)
-constexpr uint32_t TM_COLS = 256;
+constexpr uint32_t TM_A = 128;          // A operands start here
+constexpr uint32_t TM_A_H = TM_A;       // 64 cols: H [128 x 128] fp16
+constexpr uint32_t TM_A_XH = TM_A;      // 16 cols: head input [128 x 32]   (H is dead by then)
+constexpr uint32_t TM_A_XS = TM_A + 16; //  8 cols: semantic input [128 x 16]
+constexpr uint32_t TM_A_HH = TM_A;      // 32 cols: head hidden [128 x 64]  (XH / XS are dead)
+constexpr uint32_t TM_A_HS = TM_A + 32; // 32 cols: semantic hidden [128 x 64]
+constexpr uint32_t TM_COLS = 512;
 
 struct FieldIO {
   // --- inputs: either explicit points (positions/directions) or ray samples ---
@@ -131,22 +137,20 @@ __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bit
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// TMEM accumulator columns [col0, col0 + 32) of this thread's row -> ReLU -> fp16 -> the A tile
-// of the next layer (K-chunks col0/8 .. col0/8+3); `rows16` = TILE_M * 16 bytes per K-chunk.
-__device__ __forceinline__ void relu_store_32(uint32_t taddr, uint8_t* dst, int row, int col0,
-                                              __half* save_row = nullptr) {
+// TMEM accumulator columns [col0, col0 + 32) of this thread's row -> ReLU -> fp16 -> columns [col0/2, col0/2 + 16)
+// of the next layer's A operand in TMEM (a_row = this thread's lane of that operand).
+__device__ __forceinline__ void relu_store_32(uint32_t taddr, uint32_t a_row, int col0, __half* save_row = nullptr) {
   uint32_t v[32];
   ptx::tmem_ld_x32(taddr + col0, v);
   ptx::tmem_wait_ld();
+  uint32_t q[16];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 q;
-    q.x = pack_relu_h2(v[8 * j + 0], v[8 * j + 1]);
-    q.y = pack_relu_h2(v[8 * j + 2], v[8 * j + 3]);
-    q.z = pack_relu_h2(v[8 * j + 4], v[8 * j + 5]);
-    q.w = pack_relu_h2(v[8 * j + 6], v[8 * j + 7]);
-    *reinterpret_cast<uint4*>(dst + (col0 / 8 + j) * (TILE_M * 16) + row * 16) = q;
-    if (save_row) *reinterpret_cast<uint4*>(save_row + col0 + 8 * j) = q;
+  for (int j = 0; j < 16; ++j) q[j] = pack_relu_h2(v[2 * j], v[2 * j + 1]);
+  ptx::tmem_st_x16(a_row + col0 / 2, q);
+  if (save_row) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(save_row + col0 + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
   }
 }
 
@@ -158,6 +162,16 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_smem, ui
     const uint64_t ad = ptx::make_smem_desc(a_smem + k * 2 * a_lbo, a_lbo, 128);
     const uint64_t bd = ptx::make_smem_desc(w_smem + k * 2 * b_lbo, b_lbo, 128);
     ptx::mma_f16_ss(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+  }
+}
+
+// The same with the A operand in TMEM (a_tmem: first column of the operand, 8 columns per K = 16 step).
+__device__ __forceinline__ void issue_layer_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_smem, int N, int K) {
+  const uint32_t idesc = ptx::make_idesc_f16(TILE_M, N);
+  const uint32_t b_lbo = N * 16;
+  for (int k = 0; k < K / 16; ++k) {
+    const uint64_t bd = ptx::make_smem_desc(w_smem + k * 2 * b_lbo, b_lbo, 128);
+    ptx::mma_f16_ts(d_tmem, a_tmem + k * 8, bd, idesc, k > 0 ? 1u : 0u);
   }
 }
 
@@ -427,31 +441,31 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         // base layer 2
         ptx::mbar_wait(my_epi, epi_ph), epi_ph ^= 1;
         ptx::tc_fence_after();
-        issue_layer(tm + TM_MAIN, act, sW + W2_OFF, HID, HID);
+        issue_layer_ts(tm + TM_MAIN, tm + TM_A_H, sW + W2_OFF, HID, HID);
         ptx::mma_commit(my_mma);
         // base output
         ptx::mbar_wait(my_epi, epi_ph), epi_ph ^= 1;
         ptx::tc_fence_after();
-        issue_layer(tm + TM_OUT3, act, sW + W3_OFF, BASE_OUT, HID);
+        issue_layer_ts(tm + TM_OUT3, tm + TM_A_H, sW + W3_OFF, BASE_OUT, HID);
         ptx::mma_commit(my_mma);
         if (!io.density_only) {
           // head / semantic layer 1
           ptx::mbar_wait(my_epi, epi_ph), epi_ph ^= 1;
           ptx::tc_fence_after();
-          issue_layer(tm + TM_H, act + ACT_XH, sW + WH1_OFF, HID2, HEAD_IN);
-          issue_layer(tm + TM_S, act + ACT_XS, sW + WS1_OFF, HID2, SEM_IN);
+          issue_layer_ts(tm + TM_H, tm + TM_A_XH, sW + WH1_OFF, HID2, HEAD_IN);
+          issue_layer_ts(tm + TM_S, tm + TM_A_XS, sW + WS1_OFF, HID2, SEM_IN);
           ptx::mma_commit(my_mma);
           // layer 2
           ptx::mbar_wait(my_epi, epi_ph), epi_ph ^= 1;
           ptx::tc_fence_after();
-          issue_layer(tm + TM_H, act + ACT_HH, sW + WH2_OFF, HID2, HID2);
-          issue_layer(tm + TM_S, act + ACT_HS, sW + WS2_OFF, HID2, HID2);
+          issue_layer_ts(tm + TM_H, tm + TM_A_HH, sW + WH2_OFF, HID2, HID2);
+          issue_layer_ts(tm + TM_S, tm + TM_A_HS, sW + WS2_OFF, HID2, HID2);
           ptx::mma_commit(my_mma);
           // outputs
           ptx::mbar_wait(my_epi, epi_ph), epi_ph ^= 1;
           ptx::tc_fence_after();
-          issue_layer(tm + TM_HO, act + ACT_HH, sW + WH3_OFF, HEAD_OUT, HID2);
-          issue_layer(tm + TM_SO, act + ACT_HS, sW + WS3_OFF, SEM_OUT, HID2);
+          issue_layer_ts(tm + TM_HO, tm + TM_A_HH, sW + WH3_OFF, HEAD_OUT, HID2);
+          issue_layer_ts(tm + TM_SO, tm + TM_A_HS, sW + WS3_OFF, SEM_OUT, HID2);
           ptx::mma_commit(my_mma);
         }
       }
@@ -480,9 +494,9 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         {
           __half* save = (TRAIN && s < n) ? (layer == 0 ? io.save_h1 : io.save_h2) + s * io.save_stride : nullptr;
 #pragma unroll 1
-          for (int c = 0; c < HID; c += 32) relu_store_32(trow + TM_MAIN, act, row, c, save);
+          for (int c = 0; c < HID; c += 32) relu_store_32(trow + TM_MAIN, trow + TM_A_H, c, save);
         }
-        ptx::fence_proxy_async_smem();
+        ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(my_epi);
       }
@@ -534,10 +548,11 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         for (int i = 0; i < 15; ++i) hx[16 + i] = hb[1 + i];
         hx[31] = __float2half_rn(1.0f);
         const uint4* hq = reinterpret_cast<const uint4*>(hx);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(act + ACT_XH + j * (TILE_M * 16) + row * 16) = hq[j];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) *reinterpret_cast<uint4*>(act + ACT_XS + j * (TILE_M * 16) + row * 16) = hq[2 + j];
+        {
+          const uint32_t* hw = reinterpret_cast<const uint32_t*>(hx);  // 16 words = [16 SH | 15 geo | 1.0]
+          ptx::tmem_st_x16(trow + TM_A_XH, hw);
+          ptx::tmem_st_x8(trow + TM_A_XS, hw + 8);  // the semantic input is the second half: [15 geo | 1.0]
+        }
         if (TRAIN && s < n) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(io.save_xh + s * io.save_stride)[j] = hq[j];
@@ -545,7 +560,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
           for (int j = 0; j < 2; ++j) reinterpret_cast<uint4*>(io.save_xs + s * io.save_stride)[j] = hq[2 + j];
         }
       }
-      ptx::fence_proxy_async_smem();
+      ptx::tmem_wait_st();
       ptx::tc_fence_before();
       ptx::mbar_arrive(my_epi);
       // ---- head / semantic hidden layers 1 and 2
@@ -555,11 +570,11 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         ptx::tc_fence_after();
         __half* save_h = (TRAIN && s < n) ? (layer == 0 ? io.save_hh1 : io.save_hh2) + s * io.save_stride : nullptr;
         __half* save_s = (TRAIN && s < n) ? (layer == 0 ? io.save_hs1 : io.save_hs2) + s * io.save_stride : nullptr;
-        relu_store_32(trow + TM_H, act + ACT_HH, row, 0, save_h);
-        relu_store_32(trow + TM_H, act + ACT_HH, row, 32, save_h);
-        relu_store_32(trow + TM_S, act + ACT_HS, row, 0, save_s);
-        relu_store_32(trow + TM_S, act + ACT_HS, row, 32, save_s);
-        ptx::fence_proxy_async_smem();
+        relu_store_32(trow + TM_H, trow + TM_A_HH, 0, save_h);
+        relu_store_32(trow + TM_H, trow + TM_A_HH, 32, save_h);
+        relu_store_32(trow + TM_S, trow + TM_A_HS, 0, save_s);
+        relu_store_32(trow + TM_S, trow + TM_A_HS, 32, save_s);
+        ptx::tmem_wait_st();
         ptx::tc_fence_before();
         ptx::mbar_arrive(my_epi);
       }
@@ -585,7 +600,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         if (io.state != nullptr) {
           // ---- fused compositing: the tile's rows are exchanged through shared memory
           CompositeSmem cs;
-          cs.rowbuf = act + ACT_ROWBUF;  // the last layer's MMA is complete: the activation region is free
+          cs.rowbuf = act + ACT_ROWBUF;
           cs.wbuf = reinterpret_cast<float*>(act + ACT_WBUF);
           cs.fbuf = reinterpret_cast<float*>(act + ACT_FBUF);
           cs.cbuf = act + ACT_CBUF;
