@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The suite needs libapnerf.so (the product refuses to run without it).  It normally exists -- build() made it,
+    and it travels to the GPU box -- but a fresh checkout has only sources: compile it once here (nvcc cross-compiles
+    sm_100a without a GPU)."""
+    pkg = os.path.join(ROOT, "active-perception-using-neural-radiance-fields_b200")
+    if not os.path.exists(os.path.join(pkg, "libapnerf.so")):
+        import subprocess
+
+        subprocess.run([sys.executable, os.path.join(pkg, "csrc", "build.py")], check=True, cwd=os.path.join(pkg, "csrc"))
+    yield
+
+
 @pytest.fixture(scope="session")
 def apnerf():
     import apnerf as pkg
