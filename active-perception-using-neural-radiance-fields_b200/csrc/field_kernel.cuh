@@ -2,13 +2,13 @@
 // semantic head}, 128 samples per tile, persistent CTAs (one per SM), warp-specialised:
 //
 //   warps 0-7   epilogue    thread r <-> sample row r <-> TMEM lane r: TMEM -> registers
-//                           (tcgen05.ld), ReLU, fp16, next layer's A operand -> shared memory;
+//                           (tcgen05.ld), ReLU, fp16, next layer's A operand -> TMEM (tcgen05.st);
 //                           SH-4 of the view direction; final activations and output.
 //   warps 8-9   MMA issuers one thread per chain issues tcgen05.mma / tcgen05.commit; warp 8 owns TMEM.
 //   warps 10-25 encoders    512 threads (4 levels of one sample each): 8-byte hash-table gathers (L2-resident table),
 //                           trilinear blend, fp16 features straight into the MMA's A tile.
 //
-// The 64-wide encoding and all activations stay in shared memory / TMEM; only positions come
+// The 64-wide encoding stays in shared memory and all activations in TMEM; only positions come
 // in and (density, rgb, semantic logits) go out.  All nine weight matrices (80 KB fp16) sit in
 // shared memory for the lifetime of the CTA in the UMMA K-major no-swizzle layout.
 //
