@@ -307,7 +307,22 @@ def main_sampling():
         for name, v in zip(("rgb", "rgb_var", "opacity", "depth", "depth_var", "sem"), g[:6]):
             out[f"lvl2_{name}"] = v.numpy()
         out["lvl2_n"] = np.int64(g[6])
-    print("wrappers: samples", int(out["guide_n"]), int(out["occgrid_n"]), int(out["test_n"]), int(out["lvl2_n"]))
+    # training mode (utils.py:63-219 with radiance_field.training): one chunk, STRATIFIED sampling -- the jitter
+    # torch.rand_like(near_planes) * render_step_size (occ_grid.py:158-159) is patched to the constant 0.5 here
+    # and in the test, the only way to compare a random path across implementations
+    field.train()
+    real_rand_like = torch.rand_like
+    torch.rand_like = P.half_like
+    try:
+        g = utils.render_image_with_occgrid_with_depth_guide(field, e1, rays, depth=torch.full((w * h,), 2.0), **opts)
+    finally:
+        torch.rand_like = real_rand_like
+        field.eval()
+    for name, v in zip(("rgb", "opacity", "depth", "sem"), g[:4]):
+        out[f"train_{name}"] = v.detach().numpy()
+    out["train_n"] = np.int64(g[4])
+    print("wrappers: samples", int(out["guide_n"]), int(out["occgrid_n"]), int(out["test_n"]), int(out["lvl2_n"]),
+          int(out["train_n"]))
 
     # ---- S4: OccGridEstimator._update, warm-up branch (all cells), jitter patched to the cell centre
     res = 32

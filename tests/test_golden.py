@@ -281,6 +281,40 @@ def test_cuda_render_wrappers_match_reference_python(apnerf, gold):
 
 
 @pytest.mark.gpu
+def test_cuda_training_mode_render_matches_reference_python(apnerf, gold, monkeypatch):
+    """render_image_with_occgrid_with_depth_guide with the field in TRAINING mode (utils.py:63-219: one chunk,
+    stratified sampling; the differentiable field path = apnerf_field_forward_train + torch activations).  The
+    stratified jitter is patched to 0.5 on both sides (tests/golden/patterns.py)."""
+    from apnerf import synthetic
+
+    _, cfg = gold
+    g = np.load(OPS)
+    P = _patterns()
+    dev = "cuda:0"
+    w, h = 32, 24
+    rays = apnerf.Rays(origins=torch.from_numpy(g["rays_o"]).to(dev), viewdirs=torch.from_numpy(g["rays_d"]).to(dev))
+    e1 = _ops_estimator(apnerf, cfg, 1, 1, dev)
+    f = apnerf.NGPRadianceField(synthetic.ROI_AABB, layers=2, num_semantic_classes=cfg["n_classes"])
+    synthetic.init_trained_like(f, seed=cfg["field_seeds"][0], density_gain=cfg["density_gain"])
+    f = f.to(dev).train()
+    monkeypatch.setattr(torch, "rand_like", P.half_like)
+    got = apnerf.render_image_with_occgrid_with_depth_guide(
+        f, e1, rays, near_plane=cfg["near_plane"], render_step_size=4e-3, cone_angle=cfg["cone_angle"],
+        alpha_thre=cfg["alpha_thre"], render_bkgd=torch.tensor([0.1, 0.2, 0.3], device=dev),
+        depth=torch.full((w * h,), 2.0, device=dev))
+    assert got[0].requires_grad and got[3].requires_grad  # the differentiable path was taken
+    n_ref = int(g["train_n"])
+    assert abs(int(got[4]) - n_ref) <= 0.02 * n_ref, (int(got[4]), n_ref)
+    for name, a in zip(("rgb", "opacity", "depth", "sem"), got[:4]):
+        ref = g[f"train_{name}"]
+        a = a.detach().cpu().numpy()
+        assert a.shape == ref.shape, name
+        scale = max(1.0, np.abs(ref).max())
+        assert np.median(np.abs(a - ref)) <= 1e-4 * scale, (name, np.median(np.abs(a - ref)))
+        assert np.quantile(np.abs(a - ref), 0.99) <= 3e-3 * scale, (name, np.quantile(np.abs(a - ref), 0.99))
+
+
+@pytest.mark.gpu
 def test_cuda_occupancy_update_matches_reference_python(apnerf, gold, monkeypatch):
     """OccGridEstimator._update (occ_grid.py:377-437), warm-up branch, with the cell jitter patched to the cell
     centre on both sides: EMA-max values and the binarised grid are bit-exact."""
