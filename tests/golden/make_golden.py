@@ -2,7 +2,8 @@
 
 Run (CPU only, needs /root/reference; the GPU box never runs this, it only reads the .npz files):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # reference_python_path.npz : one view + a trajectory score (~90 s)
+    python tests/golden/make_golden.py --ops    # reference_python_ops.npz  : op boundary, wrappers, update, scorers (~60 s)
 
 What executes, unmodified and imported from /root/reference:
 
