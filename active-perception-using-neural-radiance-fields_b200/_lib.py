@@ -13,7 +13,8 @@ import re
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libapnerf.so")
+# APNERF_LIB_PATH: A/B measurements of another build of the SAME C-ABI (tools/); never a fallback
+LIB_PATH = os.environ.get("APNERF_LIB_PATH") or os.path.join(_PKG_DIR, "libapnerf.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "apnerf.h")
 
 _CTYPES = {

@@ -47,7 +47,7 @@ def build(verbose=False, force=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(OUT):
-        subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"])
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart"])
     return OUT
 
 

@@ -93,6 +93,23 @@ static int fill_meta(HashGridMeta& m, int n_levels, const uint32_t* meta_host) {
   return 0;
 }
 
+// Opt-in to > 48 KB of dynamic shared memory once per (kernel instantiation, device): function attributes are
+// per device, and a process may drive several GPUs.
+template <int MODE>
+static int launch_field(const FieldIO& io, const HashGridMeta& m, const FieldConst& fc, int grid, int smem,
+                        cudaStream_t stream, const char* name) {
+  static unsigned long long attr_done = 0ull;  // bit d: set on device d
+  int dev = 0;
+  APNERF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((attr_done >> dev) & 1ull)) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
+    if (dev < 64) attr_done |= 1ull << dev;
+  }
+  field_forward_kernel<MODE><<<grid, FIELD_THREADS, smem, stream>>>(io, m, fc);
+  APNERF_CHECK_LAUNCH(name);
+  return 0;
+}
+
 }  // namespace apnerf
 
 using namespace apnerf;
@@ -145,11 +162,6 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   APNERF_REQUIRE(positions != nullptr || ray_idx != nullptr, "field_forward: no sample points given");
   APNERF_REQUIRE(density_only || positions == nullptr || directions != nullptr, "field_forward: directions missing");
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward: at most 32 semantic classes");
-  static bool attr_set = false;
-  if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
-    attr_set = true;
-  }
   FieldIO io;
   io.n = n, io.n_dev = n_dev, io.positions = positions, io.directions = directions, io.ray_idx = ray_idx;
   io.t_starts = t_starts, io.t_ends = t_ends, io.rays_o = rays_o, io.rays_d = rays_d;
@@ -160,7 +172,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   io.packed = (uint4*)packed;
   io.state = nullptr, io.n_rays_total = 0, io.rays_per_call = 1, io.alpha_thre = 0.f, io.opc_thre = 0.f;
   io.n_samp = nullptr, io.iter_samples = nullptr, io.max_samples = 0, io.s_cnt = nullptr, io.keep_flag = nullptr;
-  io.total_samples = nullptr, io.probabilistic = 0;
+  io.total_samples = nullptr, io.probabilistic = 0, io.ray_counts = nullptr;
   io.cell_ids = nullptr, io.jitter = nullptr, io.occs_old = nullptr, io.occs_new = nullptr;
   io.save_enc = io.save_h1 = io.save_h2 = io.save_xh = io.save_xs = nullptr;
   io.save_hh1 = io.save_hh2 = io.save_hs1 = io.save_hs2 = nullptr;
@@ -172,9 +184,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   if (tiles < 1) tiles = 1;
   const int sms = apnerf_num_sms();
   const int grid = (int)(tiles < sms ? tiles : sms);
-  field_forward_kernel<false><<<grid, FIELD_THREADS, FIELD_SMEM_MIN, (cudaStream_t)stream>>>(io, m, fc);
-  APNERF_CHECK_LAUNCH("field_forward_kernel");
-  return 0;
+  return launch_field<0>(io, m, fc, grid, FIELD_SMEM_MIN, (cudaStream_t)stream, "field_forward_kernel");
 }
 
 APNERF_API int apnerf_field_weight_bytes(void) { return W_BYTES; }
@@ -195,11 +205,6 @@ APNERF_API int apnerf_field_forward_train(long long n, const float* positions, c
   APNERF_REQUIRE(save_enc && save_h1 && save_h2 && save_xh && save_xs && save_hh1 && save_hh2 && save_hs1 && save_hs2,
                  "field_forward_train: all nine activation buffers are required");
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward_train: at most 32 semantic classes");
-  static bool attr_set = false;
-  if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
-    attr_set = true;
-  }
   FieldIO io;
   memset(&io, 0, sizeof(io));
   io.n = n, io.positions = positions, io.directions = directions;
@@ -218,9 +223,8 @@ APNERF_API int apnerf_field_forward_train(long long n, const float* positions, c
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const long long tiles = (n + TILE_M - 1) / TILE_M;
   const int sms = apnerf_num_sms();
-  field_forward_kernel<true><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM_MIN, (cudaStream_t)stream>>>(io, m, fc);
-  APNERF_CHECK_LAUNCH("field_forward_kernel(train)");
-  return 0;
+  return launch_field<1>(io, m, fc, (int)(tiles < sms ? tiles : sms), FIELD_SMEM_MIN, (cudaStream_t)stream,
+                         "field_forward_kernel(train)");
 }
 
 // Backward of the three MLPs (csrc/field_bwd_kernel.cuh).  weights_t: the blob of apnerf_field_forward with
@@ -267,11 +271,6 @@ APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const f
   if (n == 0) return 0;
   APNERF_REQUIRE(cell_ids && jitter && occs_old && occs_new, "occ_update: null buffer");
   APNERF_REQUIRE(occs_old != occs_new, "occ_update: occs_old must be a snapshot (cells may repeat)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
-    attr_set = true;
-  }
   FieldIO io;
   memset(&io, 0, sizeof(io));
   io.n = n, io.density_only = 1;
@@ -289,9 +288,8 @@ APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const f
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const long long tiles = (n + TILE_M - 1) / TILE_M;
   const int sms = apnerf_num_sms();
-  field_forward_kernel<false><<<(int)(tiles < sms ? tiles : sms), FIELD_THREADS, FIELD_SMEM_MIN, (cudaStream_t)stream>>>(io, m, fc);
-  APNERF_CHECK_LAUNCH("field_forward_kernel(occ_update)");
-  return 0;
+  return launch_field<0>(io, m, fc, (int)(tiles < sms ? tiles : sms), FIELD_SMEM_MIN, (cudaStream_t)stream,
+                         "field_forward_kernel(occ_update)");
 }
 
 // Field query of the device-driven renderer with the compositor fused into the epilogue: sample
@@ -304,13 +302,8 @@ APNERF_API int apnerf_field_forward_fused(const int* n_rows_dev, long long max_t
                                           const void* weights, int n_sem, float* state, int n_rays_total,
                                           int rays_per_call, float alpha_thre, float opc_thre, const int* n_samp,
                                           const int* iter_samples, int max_samples, uint8_t* keep_flag,
-                                          int* total_samples, int probabilistic, void* stream) {
+                                          int* total_samples, int probabilistic, int* ray_counts, void* stream) {
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward_fused: at most 32 semantic classes");
-  static bool attr_set = false;
-  if (!attr_set) {
-    APNERF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FIELD_SMEM));
-    attr_set = true;
-  }
   FieldIO io;
   memset(&io, 0, sizeof(io));
   io.n = max_tiles * TILE_M;  // capacity of the row buffers
@@ -319,13 +312,12 @@ APNERF_API int apnerf_field_forward_fused(const int* n_rows_dev, long long max_t
   io.state = state, io.n_rays_total = n_rays_total, io.rays_per_call = rays_per_call, io.alpha_thre = alpha_thre;
   io.opc_thre = opc_thre, io.n_samp = n_samp, io.iter_samples = iter_samples, io.max_samples = max_samples;
   io.s_cnt = s_cnt, io.keep_flag = keep_flag, io.total_samples = total_samples, io.probabilistic = probabilistic;
+  io.ray_counts = ray_counts;
   HashGridMeta m;
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward_fused: bad level table");
   FieldConst fc;
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
   const int sms = apnerf_num_sms();
   const int grid = (int)(max_tiles < 1 ? 1 : (max_tiles < sms ? max_tiles : sms));
-  field_forward_kernel<false><<<grid, FIELD_THREADS, FIELD_SMEM, (cudaStream_t)stream>>>(io, m, fc);
-  APNERF_CHECK_LAUNCH("field_forward_kernel(fused)");
-  return 0;
+  return launch_field<2>(io, m, fc, grid, FIELD_SMEM, (cudaStream_t)stream, "field_forward_kernel(fused)");
 }

@@ -107,6 +107,7 @@ struct FieldIO {
   uint8_t* keep_flag;           // [n_rays_total] out: ray stays live for the next iteration
   int* total_samples;           // [n_calls] composited (alpha_thre-visible) samples
   int probabilistic;            // accumulate the variance terms
+  int* ray_counts;              // optional [2][n_rays_total]: += samples evaluated / composited per ray (tests)
   // --- training forward (kernel instantiation TRAIN): density / rgb get the raw fp16 logits (no exp / sigmoid /
   // selector) and the activations the backward kernel needs are saved (fp16, row-major) ---
   long long save_stride;        // elements between consecutive rows of every save_* matrix (they may be column
@@ -131,10 +132,12 @@ struct FieldIO {
   float occ_scale, ema_decay;   // occ = density * occ_scale;  new = max(old * ema_decay, occ)
 };
 
+// (lo, hi) fp32 bit patterns -> ReLU -> one half2 word: a single F2FP with the .relu modifier (round-to-nearest
+// then clamp at zero equals clamp then round) instead of two FMNMX and a pack.
 __device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bits) {
-  const float a = fmaxf(__uint_as_float(a_bits), 0.f), b = fmaxf(__uint_as_float(b_bits), 0.f);
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b_bits)), "f"(__uint_as_float(a_bits)));
+  return r;
 }
 
 // TMEM accumulator columns [col0, col0 + 32) of this thread's row -> ReLU -> fp16 -> columns [col0/2, col0/2 + 16)
@@ -303,6 +306,7 @@ __device__ __forceinline__ void composite_tile(const FieldIO& io, const Composit
     const int n = io.n_samp[call];
     const bool keep = (n > 0) && (opac <= io.opc_thre) && (k == n) && (io.iter_samples[call] < io.max_samples);
     io.keep_flag[ray] = keep ? 1 : 0;
+    if (io.ray_counts) io.ray_counts[ray] += k, io.ray_counts[NR + ray] += n_vis;
   }
   chain_bar_sync(chain);  // weights of every ray of the tile are in wbuf
   // ---- phase C: group g = 8 channels; rows j < min(k, 4) of the ray take groups j, j + min(k,4), ...
@@ -334,10 +338,14 @@ __device__ __forceinline__ void composite_tile(const FieldIO& io, const Composit
   chain_bar_sync(chain);  // every reader of the scratch is done before the next tile's activations overwrite it
 }
 
-template <bool TRAIN>  // TRAIN: raw outputs + saved activations (apnerf_field_forward_train); the inference
-                       // instantiation carries none of that code
+// MODE 0: inference (per-sample outputs or packed rows); 1: training forward (raw outputs + saved activations,
+// apnerf_field_forward_train); 2: compositor fused into the epilogue (apnerf_field_forward_fused).  Each
+// instantiation carries only its own code: registers and instruction-cache footprint of the hot inference kernel
+// do not pay for the other two.
+template <int MODE>
 __global__ void __launch_bounds__(FIELD_THREADS, 1)
 field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst fc) {
+  constexpr bool TRAIN = MODE == 1, FUSED = MODE == 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -379,7 +387,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
   if (warp >= N_EPI_WARPS + N_MMA_WARPS) {
     // =============================== encoders ===============================
     const int e = threadIdx.x - (N_EPI_WARPS + N_MMA_WARPS) * 32;
-    const int row = e & (TILE_M - 1), part = e >> 7;  // this thread does levels [4*part, 4*part+4)
+    const int row = e & (TILE_M - 1), part = e >> 7;  // levels (2p, 2p+1, 2p+8, 2p+9) of sample `row`
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it % A0_STAGES;
@@ -393,24 +401,33 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
 #pragma unroll
         for (int a = 0; a < 3; ++a) x[a] = __fdiv_rn(__fsub_rn(p[a], fc.aabb[a]), ext[a]);
       }
-      uint4 q[LEVELS_PER_ENC_THREAD / 2];
+      // This thread's four levels are two 16-byte chunks of the A tile: levels (2p, 2p+1) and (2p+8, 2p+9) for
+      // part p, i.e. every part has coarse (L1-resident) and fine (L2) levels and the parts finish together.
+      // Software pipeline: two levels' gathers are always in flight while the previous level is blended.
+      // Rows past the end / padding rows encode the point (0.5, 0.5, 0.5): their A rows are never read back.
+      const int nl1 = meta.n_levels - 1;
+      const int lv[4] = {2 * part, 2 * part + 1, 2 * part + 8, 2 * part + 9};
+      uint2 f[4], va[8], vb[8];
+      float wa[3], wb[3];
+      gather_level(meta, min(lv[0], nl1), x, io.table, va, wa);
+      gather_level(meta, min(lv[1], nl1), x, io.table, vb, wb);
+      f[0] = blend_level(wa, va);
+      gather_level(meta, min(lv[2], nl1), x, io.table, va, wa);
+      f[1] = blend_level(wb, vb);
+      gather_level(meta, min(lv[3], nl1), x, io.table, vb, wb);
+      f[2] = blend_level(wa, va);
+      f[3] = blend_level(wb, vb);
 #pragma unroll
-      for (int j = 0; j < LEVELS_PER_ENC_THREAD / 2; ++j) {
-        const int l = part * LEVELS_PER_ENC_THREAD + 2 * j;
-        uint2 lo = make_uint2(0u, 0u), hi = make_uint2(0u, 0u);
-        if (valid) {
-          if (l < meta.n_levels) lo = encode_level(meta, l, x, io.table);
-          if (l + 1 < meta.n_levels) hi = encode_level(meta, l + 1, x, io.table);
-        }
-        q[j] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-      }
+      for (int j = 0; j < 4; ++j)
+        if (lv[j] > nl1) f[j] = make_uint2(0u, 0u);  // levels the grid does not have contribute zeros
+      const uint4 q[2] = {make_uint4(f[0].x, f[0].y, f[1].x, f[1].y), make_uint4(f[2].x, f[2].y, f[3].x, f[3].y)};
       ptx::mbar_wait(bar_empty + 8 * buf, ph ^ 1);  // MMA of the tile that used this slot is done
       uint8_t* a0 = smem + SM_A0 + buf * (TILE_M * ENC_DIM * 2);
 #pragma unroll
-      for (int j = 0; j < LEVELS_PER_ENC_THREAD / 2; ++j) {
-        *reinterpret_cast<uint4*>(a0 + (part * (LEVELS_PER_ENC_THREAD / 2) + j) * (TILE_M * 16) + row * 16) = q[j];
-        if (TRAIN && s < n)
-          reinterpret_cast<uint4*>(io.save_enc + s * io.save_stride)[part * (LEVELS_PER_ENC_THREAD / 2) + j] = q[j];
+      for (int j = 0; j < 2; ++j) {
+        const int chunk = part + 4 * j;
+        *reinterpret_cast<uint4*>(a0 + chunk * (TILE_M * 16) + row * 16) = q[j];
+        if (TRAIN && s < n) reinterpret_cast<uint4*>(io.save_enc + s * io.save_stride)[chunk] = q[j];
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(bar_full + 8 * buf);
@@ -587,7 +604,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();
       ptx::mbar_arrive(my_epi);  // outputs are in registers: the next tile's layer 1 may overwrite TMEM
-      if (io.state != nullptr || (valid && io.packed)) {
+      if (FUSED || (valid && io.packed)) {
         __align__(16) __half row_h[40];
         row_h[0] = dens_logit;
 #pragma unroll
@@ -597,7 +614,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         row_h[6] = row_h[7] = __ushort_as_half((unsigned short)0);
 #pragma unroll
         for (int c = 0; c < 32; ++c) row_h[8 + c] = __float2half_rn(__uint_as_float(os[c]));
-        if (io.state != nullptr) {
+        if (FUSED) {
           // ---- fused compositing: the tile's rows are exchanged through shared memory
           CompositeSmem cs;
           cs.rowbuf = act + ACT_ROWBUF;

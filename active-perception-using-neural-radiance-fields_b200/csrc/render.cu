@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
     float* __restrict__ state, float alpha_thre,
     float opc_thre, const int* __restrict__ n_samp, const int* __restrict__ iter_samples, int max_samples,
     int* __restrict__ alive_next, int* __restrict__ n_alive_acc, int* __restrict__ total_samples,
-    int* counters) {
+    int* counters, int* __restrict__ ray_counts) {
   const int n_live = counters_in[0];
   const int lane = threadIdx.x & 31;
   const int n_round = (n_live + 31) & ~31;
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
       }
       const int n = n_samp[call];
       keep = (n > 0) && (opac <= opc_thre) && (k == n) && (iter_samples[call] < max_samples);
+      if (ray_counts) ray_counts[ray] += k, ray_counts[NR + ray] += n_vis;  // parity instrumentation (tests)
     }
     // compaction of the live list (order-preserving inside a warp) + per-call live counts
     const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -717,18 +718,20 @@ APNERF_API int apnerf_render_composite(int max_live, int n_rays, int rays_per_ca
                                        float alpha_thre, float opc_thre,
                                        const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
                                        int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
-                                       void* stream) {
+                                       int* ray_counts, void* stream) {
   if (max_live == 0) return 0;
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= 32, "render_composite: at most 32 semantic classes");
   const int grid = grid_for(max_live, 128, 16);
   if (probabilistic)
     render_composite_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
         counters, n_rays, rays_per_call, n_sem, alive, entry_base, entry_cnt, s_ts, s_te, (const uint4*)rows,
-        state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters);
+        state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters,
+        ray_counts);
   else
     render_composite_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
         counters, n_rays, rays_per_call, n_sem, alive, entry_base, entry_cnt, s_ts, s_te, (const uint4*)rows,
-        state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters);
+        state, alpha_thre, opc_thre, n_samp, iter_samples, max_samples, alive_next, n_alive_acc, total_samples, counters,
+        ray_counts);
   APNERF_CHECK_LAUNCH("render_composite_kernel");
   return 0;
 }

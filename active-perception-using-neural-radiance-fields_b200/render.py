@@ -109,13 +109,15 @@ class FusedRenderer:
                rays_per_call: int, *, max_samples: int = 1024, near_plane: float = 0.0, far_plane: float = 1e10,
                render_step_size: float = 1e-3, cone_angle: float = 0.0, alpha_thre: float = 0.0,
                early_stop_eps: float = 1e-4, probabilistic: bool = True, state: Optional[Tensor] = None,
-               poll_every: int = 4, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False):
+               poll_every: int = 4, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False,
+               ray_counts: Optional[Tensor] = None):
         """Render n_rays = n_calls * rays_per_call rays into the state [9 + C, n_rays] (un-finalised: see
         ``finalize``).  A generator: it enqueues one marching iteration on the CURRENT stream per ``next()``
         and yields the state tensor, so a caller can interleave several renders on different streams.
         The device decides everything; the host only (a) stays at most ~2 * poll_every iterations ahead of
         the GPU and (b) looks at the live-ray counter (pinned memory, copies enqueued every ``poll_every``
-        iterations) to stop enqueuing once every ray has terminated."""
+        iterations) to stop enqueuing once every ray has terminated.  ``ray_counts`` (int32 [2, n_rays], zeroed
+        by the caller) accumulates per ray the samples evaluated / composited: test instrumentation."""
         import ctypes
 
         ahead = 2
@@ -170,7 +172,7 @@ class FusedRenderer:
                         self.s_ts, self.s_te, rays_o, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights,
                         self.n_sem, state, n_rays, rays_per_call, float(alpha_thre), opc_thre, self.n_samp,
                         self.iter_samples, int(max_samples), self.keep_flag, self.total_samples,
-                        1 if probabilistic else 0))
+                        1 if probabilistic else 0, ray_counts))
                     steps.append(PreparedCall(
                         "apnerf_render_compact", n_rays, rays_per_call, cur, self.keep_flag, nxt, self.n_alive_acc,
                         self.chain, self.counters))
@@ -188,7 +190,7 @@ class FusedRenderer:
                         "apnerf_render_composite", n_rays, n_rays, rays_per_call, self.n_sem, cur, self.entry_base,
                         self.entry_cnt, self.s_ts, self.s_te, self.rows, state, float(alpha_thre), opc_thre,
                         self.n_samp, self.iter_samples, int(max_samples), nxt, self.n_alive_acc, self.total_samples,
-                        self.counters, 1 if probabilistic else 0))
+                        self.counters, 1 if probabilistic else 0, ray_counts))
                 seq.append(steps)
             for it in range(max_iters):
                 steps = seq[it % 2]

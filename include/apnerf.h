@@ -214,13 +214,15 @@ int apnerf_render_march(int max_live, int rays_per_call, const int* alive, const
                         int* counters, void* stream);
 /* utils.py:937-1009: weights with prefix transmittance, alpha_thre filter, accumulation, variance
  * terms, next ray mask, live-list compaction.  rows: the field kernel's packed fp16 rows
- * [s][40]; density = exp(logit - 1) (ngp.py:79), rgb = sigmoid(logit) (ngp.py:211-212). */
+ * [s][40]; density = exp(logit - 1) (ngp.py:79), rgb = sigmoid(logit) (ngp.py:211-212).
+ * ray_counts (may be NULL): int32 [2][n_rays], += per ray the samples evaluated / composited after the
+ * alpha_thre filter -- the discrete decisions of a render, which the parity tests compare with the oracle's. */
 int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_sem,
                             const int* alive, const int* entry_base, const int* entry_cnt,
                             const float* s_ts, const float* s_te, const void* rows, float* state, float alpha_thre, float opc_thre,
                             const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
                             int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
-                            void* stream);
+                            int* ray_counts, void* stream);
 
 /* Fused form of one marching iteration (kernels 1 + 2 + 3 + 4 in three launches): the compositor
  * of utils.py:937-1009 runs inside the field kernel's epilogue, so per-sample network outputs
@@ -246,7 +248,7 @@ int apnerf_field_forward_fused(const int* n_rows_dev, long long max_tiles, const
                                const void* weights, int n_sem, float* state, int n_rays_total,
                                int rays_per_call, float alpha_thre, float opc_thre, const int* n_samp,
                                const int* iter_samples, int max_samples, uint8_t* keep_flag,
-                               int* total_samples, int probabilistic, void* stream);
+                               int* total_samples, int probabilistic, int* ray_counts, void* stream);
 int apnerf_render_compact(int max_live, int rays_per_call, const int* alive, const uint8_t* keep_flag,
                           int* alive_next, int* n_alive_acc, void* chain, int* counters, void* stream);
 /* utils.py:1012-1032: background, depth normalisation, [n_rays, D] outputs (any may be NULL). */

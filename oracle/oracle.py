@@ -423,11 +423,15 @@ def subsample_indices(n_total, n_keep):
 def render_probablistic_image_with_occgrid_test(max_samples, field_fn, binaries, aabbs, rays_o, rays_d,
                                                 num_semantic_classes, near_plane=0.0, far_plane=1e10,
                                                 render_step_size=1e-3, render_bkgd=None, cone_angle=0.0,
-                                                alpha_thre=0.0, early_stop_eps=1e-4, trace=None):
+                                                alpha_thre=0.0, early_stop_eps=1e-4, trace=None, ray_counts=None):
     """field_fn(positions, dirs) -> (rgb [N,3], sigma [N,1], sem [N,C]).  Returns
     (rgb, rgb_var, opacity, depth, depth_var, sem, total_samples).  ``trace`` (a list) receives
     one dict per marching iteration (n_alive, n_samples, ray_indices, t_starts, t_ends) so the
-    fused GPU path's device-side schedule can be compared step by step."""
+    fused GPU path's device-side schedule can be compared step by step.  ``ray_counts`` (a dict)
+    receives per-ray int64 totals ``evaluated`` (samples marched and sent through the field) and
+    ``visible`` (samples that passed alpha_thre and were composited): two renders took the same
+    discrete decisions for a ray iff both totals agree (the parity tests' definition of a
+    threshold-flip ray)."""
     rays_o, rays_d = _f32(rays_o), _f32(rays_d)
     num_rays = rays_o.shape[0]
     C = num_semantic_classes
@@ -470,6 +474,10 @@ def render_probablistic_image_with_occgrid_test(max_samples, field_fn, binaries,
         if trace is not None:
             trace.append(dict(n_alive=n_alive, n_samples=n_samples, ray_indices=ray_indices.copy(),
                               t_starts=t_starts.copy(), t_ends=t_ends.copy()))
+        if ray_counts is not None:
+            ray_counts.setdefault("evaluated", np.zeros(num_rays, np.int64))
+            ray_counts.setdefault("visible", np.zeros(num_rays, np.int64))
+            ray_counts["evaluated"] += np.bincount(ray_indices, minlength=num_rays)
         positions = rays_o[ray_indices] + rays_d[ray_indices] * (t_starts[:, None] + t_ends[:, None]) / np.float32(2.0)
         if positions.shape[0] == 0:
             rgbs = np.zeros((0, 3), np.float32)
@@ -485,6 +493,8 @@ def render_probablistic_image_with_occgrid_test(max_samples, field_fn, binaries,
             vis = alphas >= np.float32(alpha_thre)
             ray_indices, rgbs, weights, t_starts, t_ends, sems = (
                 ray_indices[vis], rgbs[vis], weights[vis], t_starts[vis], t_ends[vis], sems[vis])
+        if ray_counts is not None:
+            ray_counts["visible"] += np.bincount(ray_indices, minlength=num_rays)
         t_mid = (t_starts + t_ends)[:, None] / np.float32(2.0)
         accumulate_along_rays_(weights, rgbs, ray_indices, rgb)
         accumulate_along_rays_(weights, None, ray_indices, opacity)
