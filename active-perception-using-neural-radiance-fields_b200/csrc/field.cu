@@ -164,7 +164,7 @@ APNERF_API int apnerf_field_forward(long long n, const int* n_dev, const float* 
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward: at most 32 semantic classes");
   FieldIO io;
   io.n = n, io.n_dev = n_dev, io.positions = positions, io.directions = directions, io.ray_idx = ray_idx;
-  io.t_starts = t_starts, io.t_ends = t_ends, io.rays_o = rays_o, io.rays_d = rays_d;
+  io.t_starts = t_starts, io.t_ends = t_ends, io.rays_o = rays_o, io.rays_d = rays_d, io.x01 = nullptr;
   io.table = (const uint2*)table, io.weights = (const uint4*)weights;
   io.density = density, io.rgb = rgb, io.rgb_row = rgb_row, io.rgb_ch = rgb_ch;
   io.sem = sem, io.sem_row = sem_row, io.sem_ch = sem_ch, io.feat = (__half*)feat, io.n_sem = sem ? n_sem : 0;
@@ -292,22 +292,47 @@ APNERF_API int apnerf_occ_update(long long n, const long long* cell_ids, const f
                          "field_forward_kernel(occ_update)");
 }
 
-// Field query of the device-driven renderer with the compositor fused into the epilogue: sample
-// rows (s_ray, s_cnt, s_ts, s_te; *n_rows_dev rows, a multiple of 128, rays never straddle a tile)
-// -> per-ray state update + keep flags.  Replaces apnerf_field_forward + apnerf_render_composite.
+// Field query of the device-driven renderer on the marcher's sample rows (s_ray: ray id, -1 = padding; s_x: the
+// sample's aabb-normalised point, written by apnerf_render_march*): one 80-byte row of raw fp16 network outputs per
+// sample for apnerf_render_composite.  *n_rows_dev rows (clamped to max_tiles * 128).
+APNERF_API int apnerf_field_forward_rows(const int* n_rows_dev, long long max_tiles, const int* s_ray, const void* s_x,
+                                         const float* rays_d, const float* aabb_host, int n_levels,
+                                         const uint32_t* meta_host, const void* table, const void* weights,
+                                         void* packed, void* stream) {
+  APNERF_REQUIRE(n_rows_dev && s_ray && s_x && rays_d && packed, "field_forward_rows: null buffer");
+  FieldIO io;
+  memset(&io, 0, sizeof(io));
+  io.n = max_tiles * TILE_M;  // capacity of the row buffers
+  io.n_dev = n_rows_dev, io.ray_idx = s_ray, io.x01 = (const float4*)s_x, io.rays_d = rays_d;
+  io.table = (const uint2*)table, io.weights = (const uint4*)weights, io.packed = (uint4*)packed;
+  io.rays_per_call = 1;
+  HashGridMeta m;
+  APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward_rows: bad level table");
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
+  const int sms = apnerf_num_sms();
+  const int grid = (int)(max_tiles < 1 ? 1 : (max_tiles < sms ? max_tiles : sms));
+  return launch_field<3>(io, m, fc, grid, FIELD_SMEM_MIN, (cudaStream_t)stream, "field_forward_kernel(rows)");
+}
+
+// The same with the compositor fused into the epilogue: sample rows (s_ray, s_cnt, s_ts, s_te, s_x; *n_rows_dev
+// rows, a multiple of 128, rays never straddle a tile) -> per-ray state update + keep flags.  Replaces
+// apnerf_field_forward_rows + apnerf_render_composite.
 APNERF_API int apnerf_field_forward_fused(const int* n_rows_dev, long long max_tiles, const int* s_ray,
-                                          const uint8_t* s_cnt, const float* s_ts, const float* s_te,
-                                          const float* rays_o, const float* rays_d, const float* aabb_host,
+                                          const uint8_t* s_cnt, const float* s_ts, const float* s_te, const void* s_x,
+                                          const float* rays_d, const float* aabb_host,
                                           int n_levels, const uint32_t* meta_host, const void* table,
                                           const void* weights, int n_sem, float* state, int n_rays_total,
                                           int rays_per_call, float alpha_thre, float opc_thre, const int* n_samp,
                                           const int* iter_samples, int max_samples, uint8_t* keep_flag,
                                           int* total_samples, int probabilistic, int* ray_counts, void* stream) {
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT, "field_forward_fused: at most 32 semantic classes");
+  APNERF_REQUIRE(n_rows_dev && s_ray && s_cnt && s_ts && s_te && s_x && rays_d && state, "field_forward_fused: null buffer");
   FieldIO io;
   memset(&io, 0, sizeof(io));
   io.n = max_tiles * TILE_M;  // capacity of the row buffers
-  io.n_dev = n_rows_dev, io.ray_idx = s_ray, io.t_starts = s_ts, io.t_ends = s_te, io.rays_o = rays_o, io.rays_d = rays_d;
+  io.n_dev = n_rows_dev, io.ray_idx = s_ray, io.t_starts = s_ts, io.t_ends = s_te, io.rays_d = rays_d;
+  io.x01 = (const float4*)s_x;
   io.table = (const uint2*)table, io.weights = (const uint4*)weights, io.n_sem = n_sem;
   io.state = state, io.n_rays_total = n_rays_total, io.rays_per_call = rays_per_call, io.alpha_thre = alpha_thre;
   io.opc_thre = opc_thre, io.n_samp = n_samp, io.iter_samples = iter_samples, io.max_samples = max_samples;

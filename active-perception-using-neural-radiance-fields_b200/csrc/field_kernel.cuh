@@ -80,6 +80,8 @@ struct FieldIO {
   const float* t_ends;          // [n]
   const float* rays_o;          // [n_rays, 3]
   const float* rays_d;          // [n_rays, 3]
+  const float4* x01;            // optional [n]: the samples' aabb-normalised points, written by the renderer's marcher
+                                // (same arithmetic as below, so the kernel need not re-derive them 5x per sample)
   // --- parameters ---
   const uint2* table;           // fp16 [entries, 4]
   const uint4* weights;         // W_BYTES blob in UMMA layout
@@ -338,14 +340,17 @@ __device__ __forceinline__ void composite_tile(const FieldIO& io, const Composit
   chain_bar_sync(chain);  // every reader of the scratch is done before the next tile's activations overwrite it
 }
 
-// MODE 0: inference (per-sample outputs or packed rows); 1: training forward (raw outputs + saved activations,
-// apnerf_field_forward_train); 2: compositor fused into the epilogue (apnerf_field_forward_fused).  Each
+// MODE 0: inference on explicit points / ray samples / occupancy cells (apnerf_field_forward, apnerf_occ_update);
+// 1: training forward (raw outputs + saved activations, apnerf_field_forward_train); 2: the renderer's sample rows
+// with the compositor fused into the epilogue (apnerf_field_forward_fused); 3: the renderer's sample rows -> packed
+// fp16 rows for the stand-alone compositor (apnerf_field_forward_rows).  Each
 // instantiation carries only its own code: registers and instruction-cache footprint of the hot inference kernel
 // do not pay for the other two.
 template <int MODE>
 __global__ void __launch_bounds__(FIELD_THREADS, 1)
 field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst fc) {
   constexpr bool TRAIN = MODE == 1, FUSED = MODE == 2;
+  constexpr bool XROWS = MODE == 2 || MODE == 3;  // renderer rows: (ray, marcher-written point) in, packed rows / state out
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -389,17 +394,27 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
     const int e = threadIdx.x - (N_EPI_WARPS + N_MMA_WARPS) * 32;
     const int row = e & (TILE_M - 1), part = e >> 7;  // levels (2p, 2p+1, 2p+8, 2p+9) of sample `row`
     int it = 0;
+    // marcher-written points: the next tile's point is fetched while this tile is encoded (one coalesced 16-byte
+    // load per row instead of the ray index -> origin / direction chain and three IEEE divisions per part)
+    float4 xn = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+    if (XROWS && (long long)blockIdx.x * TILE_M + row < n) xn = __ldg(io.x01 + (long long)blockIdx.x * TILE_M + row);
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int buf = it % A0_STAGES;
       const uint32_t ph = (it / A0_STAGES) & 1;
       const long long s = tile * TILE_M + row;
       float x[3] = {0.5f, 0.5f, 0.5f};
-      const bool valid = s < n && (io.ray_idx == nullptr || io.ray_idx[s] >= 0);  // padding rows carry ray -1
-      if (valid) {
-        float p[3], d[3];
-        sample_point(io, s, p, d, false);
+      if (XROWS) {
+        x[0] = xn.x, x[1] = xn.y, x[2] = xn.z;  // padding rows carry (0.5, 0.5, 0.5)
+        const long long sn = s + (long long)gridDim.x * TILE_M;
+        if (sn < n) xn = __ldg(io.x01 + sn);
+      } else {
+        const bool valid = s < n && (io.ray_idx == nullptr || io.ray_idx[s] >= 0);  // padding rows carry ray -1
+        if (valid) {
+          float p[3], d[3];
+          sample_point(io, s, p, d, false);
 #pragma unroll
-        for (int a = 0; a < 3; ++a) x[a] = __fdiv_rn(__fsub_rn(p[a], fc.aabb[a]), ext[a]);
+          for (int a = 0; a < 3; ++a) x[a] = __fdiv_rn(__fsub_rn(p[a], fc.aabb[a]), ext[a]);
+        }
       }
       // This thread's four levels are two 16-byte chunks of the A tile: levels (2p, 2p+1) and (2p+8, 2p+9) for
       // part p, i.e. every part has coarse (L1-resident) and fine (L2) levels and the parts finish together.
@@ -465,7 +480,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         ptx::tc_fence_after();
         issue_layer_ts(tm + TM_OUT3, tm + TM_A_H, sW + W3_OFF, BASE_OUT, HID);
         ptx::mma_commit(my_mma);
-        if (!io.density_only) {
+        if (XROWS || !io.density_only) {
           // head / semantic layer 1
           ptx::mbar_wait(my_epi, epi_ph), epi_ph ^= 1;
           ptx::tc_fence_after();
@@ -499,10 +514,22 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       if ((it % N_CHAINS) != chain) continue;
       const long long s = tile * TILE_M + row;
-      const bool valid = s < n && (io.ray_idx == nullptr || io.ray_idx[s] >= 0);
-      // the sample's point / direction are fetched now and consumed after two MMA round trips
+      // the sample's point / direction are fetched early and consumed after two MMA round trips; renderer rows
+      // (XROWS) read the marcher-written normalised point and only need the ray's direction
       float p[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f};
-      if (valid) sample_point(io, s, p, d, !io.density_only);
+      bool valid;
+      if (XROWS) {
+        const int ray = s < n ? io.ray_idx[s] : -1;  // padding rows carry ray -1
+        valid = ray >= 0;
+        if (valid) {
+          const float4 xs = __ldg(io.x01 + s);
+          p[0] = xs.x, p[1] = xs.y, p[2] = xs.z;  // already aabb-normalised
+          d[0] = io.rays_d[3 * (long long)ray], d[1] = io.rays_d[3 * (long long)ray + 1], d[2] = io.rays_d[3 * (long long)ray + 2];
+        }
+      } else {
+        valid = s < n && (io.ray_idx == nullptr || io.ray_idx[s] >= 0);
+        if (valid) sample_point(io, s, p, d, !io.density_only);
+      }
       // ---- base layers 1 and 2 -> H
 #pragma unroll 1
       for (int layer = 0; layer < 2; ++layer) {
@@ -531,25 +558,25 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
         inside = true;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          const float xa = __fdiv_rn(__fsub_rn(p[a], fc.aabb[a]), ext[a]);
+          const float xa = XROWS ? p[a] : __fdiv_rn(__fsub_rn(p[a], fc.aabb[a]), ext[a]);
           inside = inside && (xa > 0.0f) && (xa < 1.0f);
         }
         // density = exp(x - 1) * selector  (ngp.py:79,191-193; fp16 network output upcast first)
         const float dens = inside ? expf(__fsub_rn(__half2float(hb[0]), 1.0f)) : 0.0f;
-        if (io.density) io.density[s] = TRAIN ? __half2float(hb[0]) : dens;
-        if (io.occs_new) {
+        if (!XROWS && io.density) io.density[s] = TRAIN ? __half2float(hb[0]) : dens;
+        if (!XROWS && io.occs_new) {
           // occs[cell] = maximum(occs[cell] * ema_decay, occ); a NaN result restores the old value (:405-434)
           const long long id = io.cell_ids[s];
           const float old = io.occs_old[id];
           const float od = __fmul_rn(old, io.ema_decay), v = __fmul_rn(dens, io.occ_scale);
           io.occs_new[id] = (od != od || v != v) ? old : fmaxf(od, v);
         }
-        if (io.feat) {
+        if (!XROWS && io.feat) {
 #pragma unroll
           for (int i = 0; i < 15; ++i) io.feat[s * 15 + i] = hb[1 + i];
         }
       }
-      if (io.density_only) {
+      if (!XROWS && io.density_only) {
         ptx::tc_fence_before();
         ptx::mbar_arrive(my_epi);  // TMEM columns may be overwritten by this chain's next tile
         continue;
@@ -604,7 +631,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       ptx::tmem_wait_ld();
       ptx::tc_fence_before();
       ptx::mbar_arrive(my_epi);  // outputs are in registers: the next tile's layer 1 may overwrite TMEM
-      if (FUSED || (valid && io.packed)) {
+      if (FUSED || (valid && (XROWS || io.packed))) {
         __align__(16) __half row_h[40];
         row_h[0] = dens_logit;
 #pragma unroll
@@ -631,7 +658,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
 #pragma unroll
           for (int j = 0; j < 5; ++j) dst[j] = reinterpret_cast<const uint4*>(row_h)[j];
         }
-      } else if (valid) {
+      } else if (!XROWS && valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float v = __half2float(__float2half_rn(__uint_as_float(oh[c])));

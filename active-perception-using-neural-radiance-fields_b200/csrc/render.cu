@@ -108,6 +108,31 @@ __global__ void __launch_bounds__(256) render_init_kernel(int n_rays, int rays_p
   }
 }
 
+// The sample's aabb-normalised midpoint, op for op as perception/models/utils.py:833-836 (positions = o + d *
+// (t_start + t_end) / 2) followed by ngp.py:175-176 (x = (x - aabb_min) / (aabb_max - aabb_min)): written once per
+// sample here so that the field kernel's four encoder parts and its epilogue read it instead of re-deriving it.
+struct SamplePointer {
+  float o[3], d[3], lo[3], ext[3];
+  __device__ __forceinline__ SamplePointer(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int ray,
+                                           const FieldConst& fc) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      o[a] = rays_o[3 * (size_t)ray + a], d[a] = rays_d[3 * (size_t)ray + a];
+      lo[a] = fc.aabb[a], ext[a] = __fsub_rn(fc.aabb[3 + a], fc.aabb[a]);
+    }
+  }
+  __device__ __forceinline__ float4 at(float t0, float t1) const {
+    const float tsum = __fadd_rn(t0, t1);
+    float x[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float p = __fadd_rn(o[a], __fmul_rn(__fmul_rn(d[a], tsum), 0.5f));
+      x[a] = __fdiv_rn(__fsub_rn(p, lo[a]), ext[a]);
+    }
+    return make_float4(x[0], x[1], x[2], 0.f);
+  }
+};
+
 struct LocalSink {
   float* ts;
   float* te;
@@ -129,7 +154,7 @@ __global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counter
                                                            float cone_angle, int* __restrict__ entry_base,
                                                            int* __restrict__ entry_cnt, int* __restrict__ s_ray,
                                                            float* __restrict__ s_ts, float* __restrict__ s_te,
-                                                           int* counters) {
+                                                           FieldConst fc, float4* __restrict__ s_x, int* counters) {
   const int n_live = counters_in[0];
   const int lane = threadIdx.x & 31;
   const int n_round = (n_live + 31) & ~31;
@@ -166,10 +191,14 @@ __global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counter
     if (i < n_live) {
       entry_base[i] = base;
       entry_cnt[i] = k;
-      for (int j = 0; j < k; ++j) {
-        s_ray[base + j] = ray;
-        s_ts[base + j] = ts[j];
-        s_te[base + j] = te[j];
+      if (k > 0) {
+        const SamplePointer sp(rays_o, rays_d, ray, fc);
+        for (int j = 0; j < k; ++j) {
+          s_ray[base + j] = ray;
+          s_ts[base + j] = ts[j];
+          s_te[base + j] = te[j];
+          s_x[base + j] = sp.at(ts[j], te[j]);
+        }
       }
     }
   }
@@ -189,7 +218,8 @@ __global__ void __launch_bounds__(256) render_march_tiles_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, GridView g, const float* __restrict__ t_min,
     const float* __restrict__ t_max, const uint8_t* __restrict__ hit, float* __restrict__ near, float far_plane,
     float step_size, float cone_angle, int* __restrict__ s_ray, uint8_t* __restrict__ s_cnt,
-    float* __restrict__ s_ts, float* __restrict__ s_te, uint8_t* __restrict__ keep_flag, int s_cap, int* counters) {
+    float* __restrict__ s_ts, float* __restrict__ s_te, FieldConst fc, float4* __restrict__ s_x,
+    uint8_t* __restrict__ keep_flag, int s_cap, int* counters) {
   const int n_live = counters_in[0];
   const int lane = threadIdx.x & 31;
   const int n_round = (n_live + 31) & ~31;
@@ -242,20 +272,27 @@ __global__ void __launch_bounds__(256) render_march_tiles_kernel(
     if (lane == 31) next_pos = rows;  // the unused tail of the reservation is padding too
     if (rows > 0) {
       const int base = warp_base + pos;
-      for (int j = 0; j < k; ++j) {
-        s_ray[base + j] = ray;
-        s_cnt[base + j] = (j == 0) ? (uint8_t)k : (uint8_t)(0x80 | j);  // ray head: #samples; else: offset in ray
-        s_ts[base + j] = ts[j];
-        s_te[base + j] = te[j];
+      const float4 pad = make_float4(0.5f, 0.5f, 0.5f, 0.f);
+      if (k > 0) {
+        const SamplePointer sp(rays_o, rays_d, ray, fc);
+        for (int j = 0; j < k; ++j) {
+          s_ray[base + j] = ray;
+          s_cnt[base + j] = (j == 0) ? (uint8_t)k : (uint8_t)(0x80 | j);  // ray head: #samples; else: offset in ray
+          s_ts[base + j] = ts[j];
+          s_te[base + j] = te[j];
+          s_x[base + j] = sp.at(ts[j], te[j]);
+        }
       }
       for (int r = pos + k; r < next_pos; ++r) {
         s_ray[warp_base + r] = -1;
         s_cnt[warp_base + r] = 0;
+        s_x[warp_base + r] = pad;
       }
       if (lane == 0)  // rows skipped before the first ray (it did not fit into the partly used tile)
         for (int r = 0; r < pos; ++r) {
           s_ray[warp_base + r] = -1;
           s_cnt[warp_base + r] = 0;
+          s_x[warp_base + r] = pad;
         }
     }
   }
@@ -671,14 +708,16 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
                                    const uint8_t* binaries, const float* aabbs, const float* t_min, const float* t_max,
                                    const uint8_t* hit, float* near, float far_plane, float step_size, float cone_angle,
                                    int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
-                                   int* counters, void* stream) {
+                                   const float* field_aabb_host, void* s_x, int* counters, void* stream) {
   if (max_live == 0) return 0;
   GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = field_aabb_host[i];
   int mt, mc;
   apnerf_march_cfg(mt, mc);
   render_march_kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
-      cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, counters);
+      cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, fc, (float4*)s_x, counters);
   APNERF_CHECK_LAUNCH("render_march_kernel");
   return 0;
 }
@@ -689,14 +728,17 @@ APNERF_API int apnerf_render_march_tiles(int max_live, int rays_per_call, const 
                                          const uint8_t* binaries, const float* aabbs, const float* t_min,
                                          const float* t_max, const uint8_t* hit, float* near, float far_plane,
                                          float step_size, float cone_angle, int* s_ray, uint8_t* s_cnt, float* s_ts,
-                                         float* s_te, uint8_t* keep_flag, int s_cap, int* counters, void* stream) {
+                                         float* s_te, const float* field_aabb_host, void* s_x, uint8_t* keep_flag,
+                                         int s_cap, int* counters, void* stream) {
   if (max_live == 0) return 0;
   GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  FieldConst fc;
+  for (int i = 0; i < 6; ++i) fc.aabb[i] = field_aabb_host[i];
   int mt, mc;
   apnerf_march_cfg(mt, mc);
   render_march_tiles_kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
-      cone_angle, s_ray, s_cnt, s_ts, s_te, keep_flag, s_cap, counters);
+      cone_angle, s_ray, s_cnt, s_ts, s_te, fc, (float4*)s_x, keep_flag, s_cap, counters);
   APNERF_CHECK_LAUNCH("render_march_tiles_kernel");
   return 0;
 }

@@ -75,6 +75,7 @@ class FusedRenderer:
             self.s_ray = torch.empty(s_cap, device=dev, dtype=torch.int32)
             self.s_ts = torch.empty(s_cap, device=dev)
             self.s_te = torch.empty(s_cap, device=dev)
+            self.s_x = torch.empty((s_cap, 4), device=dev)  # aabb-normalised sample points (marcher -> field kernel)
             self._cap_samples = s_cap
         if need_rows and s_cap > getattr(self, "_cap_rows", 0):
             self.rows = torch.empty((s_cap, 40), device=dev, dtype=torch.float16)  # raw fp16 network outputs
@@ -166,10 +167,10 @@ class FusedRenderer:
                         "apnerf_render_march_tiles", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry,
                         rz, binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
                         float(render_step_size), float(cone_angle), self.s_ray, self.s_cnt, self.s_ts, self.s_te,
-                        self.keep_flag, int(s_cap), self.counters))
+                        aabb_p, self.s_x, self.keep_flag, int(s_cap), self.counters))
                     steps.append(PreparedCall(
                         "apnerf_field_forward_fused", self.counters[2:3], s_cap // 128, self.s_ray, self.s_cnt,
-                        self.s_ts, self.s_te, rays_o, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights,
+                        self.s_ts, self.s_te, self.s_x, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights,
                         self.n_sem, state, n_rays, rays_per_call, float(alpha_thre), opc_thre, self.n_samp,
                         self.iter_samples, int(max_samples), self.keep_flag, self.total_samples,
                         1 if probabilistic else 0, ray_counts))
@@ -181,11 +182,10 @@ class FusedRenderer:
                         "apnerf_render_march", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry, rz,
                         binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
                         float(render_step_size), float(cone_angle), self.entry_base, self.entry_cnt, self.s_ray,
-                        self.s_ts, self.s_te, self.counters))
+                        self.s_ts, self.s_te, aabb_p, self.s_x, self.counters))
                     steps.append(PreparedCall(
-                        "apnerf_field_forward", 0, self.counters[2:3], None, None, self.s_ray, self.s_ts, self.s_te,
-                        rays_o, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights, None, None, 0, 0, None,
-                        0, 0, self.n_sem, None, self.rows, 0, (s_cap + 127) // 128))
+                        "apnerf_field_forward_rows", self.counters[2:3], (s_cap + 127) // 128, self.s_ray, self.s_x,
+                        rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights, self.rows))
                     steps.append(PreparedCall(
                         "apnerf_render_composite", n_rays, n_rays, rays_per_call, self.n_sem, cur, self.entry_base,
                         self.entry_cnt, self.s_ts, self.s_te, self.rows, state, float(alpha_thre), opc_thre,

@@ -60,19 +60,35 @@ def quat_xyzw_to_matrix(q):
     ], dtype=np.float64)
 
 
-def make_poses(n_views, seed=3, aabb=ROI_AABB, margin=1.0, height=1.5):
-    """[n_views, 7] float64 poses (x, y, z, qx, qy, qz, qw): positions uniform in the aabb shrunk by
-    `margin` at y = `height`, yaw uniform in [0, 2 pi) about +y (planner pose format,
-    planning/planning_funcs.py:222-399)."""
-    rng = np.random.default_rng(seed)
-    poses = np.zeros((n_views, 7))
-    poses[:, 0] = rng.uniform(-0.5, 0.5, n_views)
-    poses[:, 1] = height
-    poses[:, 2] = rng.uniform(-0.5, 0.5, n_views)
-    yaw = rng.uniform(0, 2 * np.pi, n_views)
+def _poses(x, z, yaw, height):
+    poses = np.zeros((len(x), 7))
+    poses[:, 0], poses[:, 1], poses[:, 2] = x, height, z
     poses[:, 4] = np.sin(yaw / 2)
     poses[:, 6] = np.cos(yaw / 2)
     return poses
+
+
+def make_poses(n_views, seed=3, aabb=ROI_AABB, margin=1.0, height=1.5):
+    """[n_views, 7] float64 poses (x, y, z, qx, qy, qz, qw), SURVEY.md section 8(d)-3: positions uniform in the
+    aabb shrunk by `margin` metres in x and z, at y = `height`; yaw uniform in [0, 2 pi) about +y (planner pose
+    format, planning/planning_funcs.py:222-399).  Cameras may start inside an occupied cell: such views march
+    samples from the near plane on, as the reference would."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(aabb[0] + margin, aabb[3] - margin, n_views)
+    z = rng.uniform(aabb[2] + margin, aabb[5] - margin, n_views)
+    yaw = rng.uniform(0, 2 * np.pi, n_views)
+    return _poses(x, z, yaw, height)
+
+
+def make_poses_corridor(n_views, seed=3, half_width=0.5, height=1.5):
+    """Poses inside the free corridor make_occupancy() keeps around the scene centre (x, z uniform in
+    [-half_width, half_width]): the round-1 distribution, kept for the golden fixtures (tests/golden/) and the
+    small-scene tests whose scenario needs a camera in free space."""
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-half_width, half_width, n_views)
+    z = rng.uniform(-half_width, half_width, n_views)
+    yaw = rng.uniform(0, 2 * np.pi, n_views)
+    return _poses(x, z, yaw, height)
 
 
 def pose_to_matrix(pose7):

@@ -205,13 +205,15 @@ int apnerf_render_init(int n_rays, int rays_per_call, const float* rays_o, const
 int apnerf_render_schedule(int n_calls, int rays_per_call, int max_samples, int min_samples,
                            int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, void* stream);
 /* utils.py:906-929: limited traversal of every live ray from its last terminate plane;
- * emits the compact sample list (s_ray, s_ts, s_te), counters[2] and per-entry (base, count). */
+ * emits the compact sample list (s_ray, s_ts, s_te), counters[2] and per-entry (base, count), plus
+ * s_x [rows] float4: every sample's midpoint o + d (t_s + t_e) / 2 (utils.py:833-836) normalised by the
+ * FIELD's aabb (ngp.py:175-176; field_aabb_host: 6 floats on the host) for apnerf_field_forward_rows. */
 int apnerf_render_march(int max_live, int rays_per_call, const int* alive, const int* n_samp,
                         const float* rays_o, const float* rays_d, int rx, int ry, int rz,
                         const uint8_t* binaries, const float* aabbs, const float* t_min, const float* t_max,
                         const uint8_t* hit, float* near, float far_plane, float step_size, float cone_angle,
                         int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
-                        int* counters, void* stream);
+                        const float* field_aabb_host, void* s_x, int* counters, void* stream);
 /* utils.py:937-1009: weights with prefix transmittance, alpha_thre filter, accumulation, variance
  * terms, next ray mask, live-list compaction.  rows: the field kernel's packed fp16 rows
  * [s][40]; density = exp(logit - 1) (ngp.py:79), rgb = sigmoid(logit) (ngp.py:211-212).
@@ -223,6 +225,16 @@ int apnerf_render_composite(int max_live, int n_rays, int rays_per_call, int n_s
                             const int* n_samp, const int* iter_samples, int max_samples, int* alive_next,
                             int* n_alive_acc, int* total_samples, int* counters, int probabilistic,
                             int* ray_counts, void* stream);
+
+/* The renderer's field query (kernels 2 + 3) on the marcher's sample rows: s_ray [rows] (ray id, -1 = padding row),
+ * s_x [rows] float4 (aabb-normalised sample point written by apnerf_render_march), rays_d [n_rays,3] -> packed:
+ * one 80-byte row of raw fp16 network outputs per sample (layout under apnerf_field_forward) for
+ * apnerf_render_composite.  *n_rows_dev rows, clamped to max_tiles * 128.  Replaces, per marching iteration,
+ * radiance_field(positions, t_dirs) at perception/models/utils.py:931-935 (ngp.py:222-238 + tcnn). */
+int apnerf_field_forward_rows(const int* n_rows_dev, long long max_tiles, const int* s_ray, const void* s_x,
+                              const float* rays_d, const float* aabb_host, int n_levels,
+                              const uint32_t* meta_host, const void* table, const void* weights, void* packed,
+                              void* stream);
 
 /* Fused form of one marching iteration (kernels 1 + 2 + 3 + 4 in three launches): the compositor
  * of utils.py:937-1009 runs inside the field kernel's epilogue, so per-sample network outputs
@@ -240,10 +252,11 @@ int apnerf_render_march_tiles(int max_live, int rays_per_call, const int* alive,
                               const uint8_t* binaries, const float* aabbs, const float* t_min,
                               const float* t_max, const uint8_t* hit, float* near, float far_plane,
                               float step_size, float cone_angle, int* s_ray, uint8_t* s_cnt, float* s_ts,
-                              float* s_te, uint8_t* keep_flag, int s_cap, int* counters, void* stream);
+                              float* s_te, const float* field_aabb_host, void* s_x, uint8_t* keep_flag, int s_cap,
+                              int* counters, void* stream);
 int apnerf_field_forward_fused(const int* n_rows_dev, long long max_tiles, const int* s_ray,
-                               const uint8_t* s_cnt, const float* s_ts, const float* s_te,
-                               const float* rays_o, const float* rays_d, const float* aabb_host,
+                               const uint8_t* s_cnt, const float* s_ts, const float* s_te, const void* s_x,
+                               const float* rays_d, const float* aabb_host,
                                int n_levels, const uint32_t* meta_host, const void* table,
                                const void* weights, int n_sem, float* state, int n_rays_total,
                                int rays_per_call, float alpha_thre, float opc_thre, const int* n_samp,

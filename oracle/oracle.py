@@ -291,7 +291,7 @@ def hashgrid_meta(n_levels=16, base_resolution=16, max_resolution=4096, log2_has
     return meta, off
 
 
-def hashgrid_encode(x01, table_half, meta, want_indices=False):
+def hashgrid_encode(x01, table_half, meta, want_indices=False, parallel=True):
     """x01 [N,3] fp32 -> fp16 features [N, L*4] (+ table entry indices [N,L,8])."""
     x01 = _f32(x01)
     n = x01.shape[0]
@@ -306,17 +306,24 @@ def hashgrid_encode(x01, table_half, meta, want_indices=False):
         L.apo_hashgrid_encode(ctypes.c_int64(s0), ctypes.c_int64(s1), _p(x01), ctypes.c_int32(L_), _p(meta),
                               _p(table), _p(out), _p(idx))
 
-    _parallel(n, run, grain=256)
+    if parallel:
+        _parallel(n, run, grain=256)
+    elif n:
+        run(0, n)
     enc = out.view(np.float16)
     return (enc, idx) if want_indices else enc
 
 
-def sh4(dirs):
+def sh4(dirs, parallel=True):
     dirs = _f32(dirs)
     n = dirs.shape[0]
     out = np.empty((n, 16), np.uint16)
     L = lib()
-    _parallel(n, lambda s0, s1: L.apo_sh4(ctypes.c_int64(s0), ctypes.c_int64(s1), _p(dirs), _p(out)))
+    run = lambda s0, s1: L.apo_sh4(ctypes.c_int64(s0), ctypes.c_int64(s1), _p(dirs), _p(out))
+    if parallel:
+        _parallel(n, run)
+    elif n:
+        run(0, n)
     return out.view(np.float16)
 
 
@@ -367,13 +374,53 @@ def _pad16(n):
     return (n + 15) // 16 * 16
 
 
-def field_forward(positions, directions, aabb, fp: FieldParams, density_only=False):
-    """NGPRadianceField.forward / query_density, perception/models/radiance_fields/ngp.py:171-238."""
+def field_forward(positions, directions, aabb, fp: FieldParams, density_only=False, chunk=8192):
+    """NGPRadianceField.forward / query_density, perception/models/radiance_fields/ngp.py:171-238.
+    Rows are independent, so large batches are evaluated in row chunks on host threads (numpy's fp16 <-> fp32
+    conversions are single-threaded and were 55 % of the oracle's time); per-row results do not depend on the
+    chunking (checked by tests/test_oracle.py)."""
+    n = np.asarray(positions).shape[0]
+    if n <= chunk or N_THREADS == 1:
+        return _field_forward_rows(positions, directions, aabb, fp, density_only)
+    positions = _f32(positions)
+    directions = None if directions is None else _f32(directions)
+    ranges = [(i, min(n, i + chunk)) for i in range(0, n, chunk)]
+    with _blas_threads(1), ThreadPoolExecutor(min(N_THREADS, len(ranges))) as ex:
+        parts = list(ex.map(lambda r: _field_forward_rows(positions[r[0]:r[1]],
+                                                          None if directions is None else directions[r[0]:r[1]],
+                                                          aabb, fp, density_only, parallel=False), ranges))
+    if density_only:
+        return np.concatenate(parts, 0)
+    return tuple(np.concatenate([p[k] for p in parts], 0) for k in range(len(parts[0])))
+
+
+class _blas_threads:
+    """Limit the BLAS pool while our own threads run one GEMM each (threadpoolctl when present)."""
+
+    def __init__(self, n):
+        self.n, self.ctx = n, None
+
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+
+            self.ctx = threadpool_limits(limits=self.n, user_api="blas")
+            self.ctx.__enter__()
+        except Exception:
+            self.ctx = None
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+def _field_forward_rows(positions, directions, aabb, fp: FieldParams, density_only=False, parallel=True):
     positions = _f32(positions)
     aabb = _f32(aabb)
     x = (positions - aabb[:3]) / (aabb[3:] - aabb[:3])
     selector = ((x > 0.0) & (x < 1.0)).all(-1)
-    enc = hashgrid_encode(x, fp.table, fp.meta)
+    enc = hashgrid_encode(x, fp.table, fp.meta, parallel=parallel)
     base = mlp_forward(enc, fp.base_w).astype(np.float32)
     density = np.exp(base[:, :1] - np.float32(1.0)) * selector[:, None].astype(np.float32)
     if density_only:
@@ -381,7 +428,7 @@ def field_forward(positions, directions, aabb, fp: FieldParams, density_only=Fal
     feat = base[:, 1:1 + fp.geo_feat_dim].astype(np.float16)
     n = positions.shape[0]
     h = np.ones((n, fp.head_in), np.float16)  # tcnn pads inputs to a multiple of 16 with 1.0
-    h[:, :16] = sh4(directions)
+    h[:, :16] = sh4(directions, parallel=parallel)
     h[:, 16:16 + fp.geo_feat_dim] = feat
     rgb_raw = mlp_forward(h, fp.head_w).astype(np.float32)[:, :3]
     rgb = (1.0 / (1.0 + np.exp(-rgb_raw))).astype(np.float32)

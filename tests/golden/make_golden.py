@@ -183,7 +183,7 @@ def main():
     utils, Dataset, OccGridEstimator = import_reference()
     from apnerf import synthetic
     fields, ests = build_scene(OccGridEstimator)
-    traj = synthetic.make_poses(CFG["traj_len"], seed=CFG["pose_seed"])
+    traj = synthetic.make_poses_corridor(CFG["traj_len"], seed=CFG["pose_seed"])
     focal = CFG["img_w"] / 2.0
 
     # ---- fixture 1: one view through utils.render_probablistic_image_with_occgrid_test, two option sets
@@ -250,7 +250,7 @@ def main_sampling():
     from datasets.utils import Rays
     from nerfacc.volrend import rendering
     out = {}
-    traj = synthetic.make_poses(4, seed=CFG["pose_seed"])
+    traj = synthetic.make_poses_corridor(4, seed=CFG["pose_seed"])
     w, h = 32, 24
     pose = torch.from_numpy(synthetic.pose_to_matrix(traj[1])).unsqueeze(0).float()
     K = np.array([[w / 2.0, 0, w / 2], [0, w / 2.0, h / 2], [0, 0, 1.0]])
@@ -344,7 +344,7 @@ def main_sampling():
     # ActiveNeRFMapper.trajector_uncertainty (pipeline.py:800-916).  The reference's own tuple unpacking (:823 wants
     # 4 values from member 0, :842 wants 3 from the others) only works for ONE member with semantic classes, so
     # that is the configuration pinned here.
-    traj = synthetic.make_poses(22, seed=CFG["pose_seed"] + 1)
+    traj = synthetic.make_poses_corridor(22, seed=CFG["pose_seed"] + 1)
     focal = CFG["img_w"] / 2.0
     res = Dataset.render_image_from_pose(field, e1, traj[:3], CFG["img_w"], CFG["img_h"], focal, CFG["near_plane"],
                                          CFG["render_step_size"], CFG["scale"], CFG["cone_angle"], CFG["alpha_thre"], 4, "cpu")

@@ -31,7 +31,7 @@ def _rays(apnerf, w, h, pose_seed=3):
     from apnerf import synthetic
     from oracle import oracle as O
 
-    pose = synthetic.pose_to_matrix(synthetic.make_poses(1, seed=pose_seed)[0]).astype(np.float32)
+    pose = synthetic.pose_to_matrix(synthetic.make_poses_corridor(1, seed=pose_seed)[0]).astype(np.float32)
     o, d = O.generate_image_rays(pose, w, h, focal=w / 2)
     return o, d, pose
 
@@ -47,7 +47,7 @@ def test_generate_rays_matches_reference_formula(apnerf, oracle):
     from apnerf import synthetic
     from apnerf._lib import call
 
-    poses = synthetic.make_poses(3, seed=9)
+    poses = synthetic.make_poses_corridor(3, seed=9)
     c2w = torch.from_numpy(apnerf.scoring.poses_to_c2w(poses)).to(DEV)
     w, h = 64, 48
     ro = torch.empty((3 * w * h, 3), device=DEV)
@@ -193,7 +193,7 @@ def test_score_trajectories_end_to_end(apnerf, oracle):
     f1 = f1.to(DEV).eval()
     w, h = 24, 18
     scorer = apnerf.PredictiveInformationScorer([f0, f1], [e0, e0], w, h, w / 2, views_per_batch=3, **OPTS)
-    poses = synthetic.make_poses(5, seed=21)
+    poses = synthetic.make_poses_corridor(5, seed=21)
     view_traj = np.array([0, 0, 0, 1, 1], dtype=np.int32)
     terms = scorer.score_views(poses, view_traj, 2)
     outs = [[], []]

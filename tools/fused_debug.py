@@ -9,7 +9,7 @@ est.binaries = synthetic.make_occupancy(128, seed=1); est = est.to(dev).eval()
 f = apnerf.NGPRadianceField(synthetic.ROI_AABB, layers=2, num_semantic_classes=29)
 f = synthetic.init_trained_like(f, seed=2).to(dev).eval()
 V, W, H = 16, 320, 240
-c2w = torch.from_numpy(apnerf.scoring.poses_to_c2w(synthetic.make_poses(V, seed=3))).to(dev)
+c2w = torch.from_numpy(apnerf.scoring.poses_to_c2w(synthetic.make_poses_corridor(V, seed=3))).to(dev)
 ro = torch.empty((V*W*H, 3), device=dev); rd = torch.empty_like(ro)
 _lib.call("apnerf_generate_rays", V, c2w, W, H, 160.0, W*H, None, ro, rd)
 opts = dict(near_plane=0.1, render_step_size=1e-3, cone_angle=0.004, alpha_thre=0.01)
