@@ -21,7 +21,8 @@ namespace apnerf {
 
 
 // counters[0] live rays this iteration, [1] live rays being collected for the next one,
-// [2] samples emitted this iteration, [3] total iterations executed with work
+// [2] samples emitted this iteration, [3] total iterations executed with work,
+// [8] sample rows evaluated so far in this render (sum of [2] over the finished iterations; 16 ints in all)
 __global__ void render_schedule_kernel(int n_calls, int rays_per_call, int max_samples, int min_samples,
                                        int* __restrict__ n_alive_acc, int* __restrict__ n_samp,
                                        int* __restrict__ iter_samples, int* __restrict__ counters) {
@@ -38,6 +39,7 @@ __global__ void render_schedule_kernel(int n_calls, int rays_per_call, int max_s
   if (threadIdx.x == 0) {
     counters[0] = counters[1];
     counters[1] = 0;
+    counters[8] += counters[6] > 0 ? counters[6] : counters[2];  // rows of the iteration that just finished ([6]: real rows of the tile layout)
     counters[2] = 0;
     if (counters[0] > 0) counters[3] += 1;
     counters[4] = 0;  // ticket counter of render_compact_kernel
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) render_init_kernel(int n_rays, int rays_p
       iter_samples[c] = 0;
       total_samples[c] = 0;
     }
-    if (threadIdx.x == 0) counters[0] = 0, counters[1] = n_rays, counters[2] = 0, counters[3] = 0, counters[4] = 0;  // [5] (overflow) is sticky: the host clears it
+    if (threadIdx.x == 0) counters[0] = 0, counters[1] = n_rays, counters[2] = 0, counters[3] = 0, counters[4] = 0, counters[6] = 0, counters[8] = 0;  // [5] (overflow) is sticky: the host clears it
   }
 }
 

@@ -94,7 +94,7 @@ class FusedRenderer:
             self.s_cnt = torch.zeros(s_cap, device=dev, dtype=torch.uint8)
             self._cap_cnt = s_cap
         if not hasattr(self, "counters"):
-            self.counters = torch.zeros(8, device=dev, dtype=torch.int32)
+            self.counters = torch.zeros(16, device=dev, dtype=torch.int32)
             self._tag = 0
 
     @torch.no_grad()
@@ -214,7 +214,12 @@ class FusedRenderer:
                     if finished:
                         break
                 yield state
+            seq[0][0]()  # one more schedule launch folds the last iteration's rows into counters[8]
         yield state
+
+    def rows_evaluated(self) -> int:
+        """Sample rows sent through the field by the last render (host sync)."""
+        return int(self.counters[8].item())
 
     def check_overflow(self) -> None:
         """Raise if a marching iteration needed more sample rows than were allocated (host sync)."""

@@ -54,7 +54,7 @@ class PredictiveInformationScorer:
     def __init__(self, radiance_fields: Sequence[torch.nn.Module], estimators: Sequence[torch.nn.Module], width: int,
                  height: int, focal: float, *, near_plane: float = 0.1, render_step_size: float = 1e-3,
                  cone_angle: float = 0.004, alpha_thre: float = 0.01, scale: float = 1.0, max_samples: int = 1024,
-                 device="cuda:0", views_per_batch: int = 32, concurrent_batches: int = 1):
+                 device="cuda:0", views_per_batch: int = 32, concurrent_batches: int = 1, balance: str = "lpt"):
         assert 1 <= len(radiance_fields) <= 4 and len(radiance_fields) == len(estimators)
         self.fields, self.estimators = list(radiance_fields), list(estimators)
         self.width, self.height, self.focal = int(width), int(height), float(focal)
@@ -63,6 +63,10 @@ class PredictiveInformationScorer:
         self.device = torch.device(device)
         self.n_sem = self.fields[0].num_semantic_classes
         self.views_per_batch = int(views_per_batch)
+        assert balance in ("lpt", "contiguous")
+        self.balance = balance
+        self.after_render = None  # optional callable(renderer), invoked once per finished render (measurement)
+        self._probe = None
         # rounded-linspace subsample of the full image (habitat_to_data.py:462-467)
         h, w = int(height * scale), int(width * scale)
         self.rays_per_view = h * w
@@ -130,6 +134,8 @@ class PredictiveInformationScorer:
                         r = self.renderers[slot][m]
                         if not self.interleave:
                             r.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st, **self.opts)
+                            if self.after_render is not None:
+                                self.after_render(r)
                             continue
                         self._streams[slot][m].wait_event(ready)
                         gens.append((self._streams[slot][m],
@@ -146,11 +152,71 @@ class PredictiveInformationScorer:
                     done = torch.cuda.Event()
                     done.record(stream)
                     main.wait_event(done)
+                if self.after_render is not None and self.interleave:
+                    for slot in range(len(group)):
+                        for r in self.renderers[slot]:
+                            with torch.cuda.stream(main):
+                                self.after_render(r)
                 for v0, v1, nr, states in work:
                     states = states + [None] * (4 - len(states))
                     call("apnerf_score_views", E, states[0], states[1], states[2], states[3], nr, self.rays_per_view,
                          self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
         return sums
+
+    # ---- multi-GPU view assignment ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def estimate_rows(self, c2w: torch.Tensor) -> torch.Tensor:
+        """Estimated field evaluations per view ([n_views] float32, device): the views are rendered through member 0 at
+        1/64 of their rays (rounded-linspace subsample, the reference's own subsampling rule) and the sample rows
+        the marcher emitted are counted per view.  On the synthetic scene the estimate tracks the full-resolution
+        count to a few per cent while a view's cost varies 3x between poses."""
+        n_views = c2w.shape[0]
+        if self._probe is None:
+            k = int(min(self.rays_per_view, max(256, self.rays_per_view // 64)))
+            idx = np.round(np.linspace(0, self.rays_per_view - 1, k)).astype(np.int64)
+            if self.keep_idx is not None:
+                idx = self.keep_idx.cpu().numpy().astype(np.int64)[idx]
+            self._probe = dict(k=k, keep=torch.from_numpy(idx.astype(np.int32)).to(self.device),
+                               renderer=FusedRenderer(self.device, self.n_sem))
+        pr = self._probe
+        k = pr["k"]
+        n_rays = n_views * k
+        if pr.get("cap", 0) < n_rays:
+            pr["rays_o"] = torch.empty((n_rays, 3), device=self.device)
+            pr["rays_d"] = torch.empty((n_rays, 3), device=self.device)
+            pr["counts"] = torch.empty((2, n_rays), device=self.device, dtype=torch.int32)
+            pr["cap"] = n_rays
+        rays_o, rays_d = pr["rays_o"][:n_rays], pr["rays_d"][:n_rays]
+        counts = pr["counts"].view(-1)[: 2 * n_rays].view(2, n_rays)
+        counts.zero_()
+        with torch.cuda.device(self.device):
+            call("apnerf_generate_rays", n_views, c2w.contiguous(), self.width, self.height, self.focal, k, pr["keep"],
+                 rays_o, rays_d)
+            pr["renderer"].render(self.fields[0], self.estimators[0], rays_o, rays_d, k, probabilistic=False,
+                                  ray_counts=counts, **self.opts)
+        return counts[0].view(n_views, k).sum(1).float() * (self.rays_per_view / k)
+
+    def assign_views(self, poses: np.ndarray, rank: int, world: int, process_group=None) -> np.ndarray:
+        """Indices (ascending) of the views this rank renders.  world == 1 or balance == "contiguous": the contiguous
+        balanced slice.  balance == "lpt": every rank estimates the cost of its contiguous slice (``estimate_rows``),
+        the estimates are all-gathered (one small collective) and the views are dealt out longest-processing-time
+        first to the least loaded rank -- the same deterministic assignment on every rank."""
+        import torch.distributed as dist
+
+        n = len(poses)
+        lo, hi = shard_range(n, rank, world)
+        if world == 1 or self.balance == "contiguous" or n < 2 * world:
+            return np.arange(lo, hi)
+        cap = (n + world - 1) // world
+        est = torch.zeros(cap, device=self.device)
+        if hi > lo:
+            c2w = torch.from_numpy(poses_to_c2w(poses[lo:hi])).to(self.device)
+            est[: hi - lo] = self.estimate_rows(c2w)
+        gathered = [torch.empty_like(est) for _ in range(world)]
+        dist.all_gather(gathered, est, group=process_group)
+        g = torch.stack(gathered).cpu().numpy()
+        cost = np.concatenate([g[r, : shard_range(n, r, world)[1] - shard_range(n, r, world)[0]] for r in range(world)])
+        return lpt_assign(cost, world)[rank]
 
     @staticmethod
     def finish(sums: np.ndarray, pixels_per_traj: np.ndarray) -> np.ndarray:
@@ -191,13 +257,13 @@ class PredictiveInformationScorer:
         rank = dist.get_rank(process_group) if use_dist else 0
         world = dist.get_world_size(process_group) if use_dist else 1
         n_views = poses.shape[0]
-        lo, hi = shard_range(n_views, rank, world)
-        c2w_host = torch.from_numpy(poses_to_c2w(poses[lo:hi])).pin_memory()
-        vt_host = torch.from_numpy(np.ascontiguousarray(view_traj[lo:hi], dtype=np.int32)).pin_memory()
+        mine = self.assign_views(poses, rank, world, process_group)
+        c2w_host = torch.from_numpy(poses_to_c2w(poses[mine])).pin_memory()
+        vt_host = torch.from_numpy(np.ascontiguousarray(np.asarray(view_traj)[mine], dtype=np.int32)).pin_memory()
         c2w = c2w_host.to(self.device, non_blocking=True)
         vt = vt_host.to(self.device, non_blocking=True)
         sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
-        if hi > lo:
+        if len(mine):
             self.partial_sums(c2w, vt, n_traj, sums)
         sums = all_reduce_partial_sums(sums, process_group)
         counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
@@ -215,6 +281,19 @@ def all_reduce_partial_sums(sums: torch.Tensor, process_group=None) -> torch.Ten
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=process_group)
     return sums
+
+
+def lpt_assign(cost: np.ndarray, world: int):
+    """Longest-processing-time-first assignment of units with the given costs to `world` bins; returns one ascending
+    index array per bin.  Deterministic (stable sort, ties to the lower bin), so every rank computes the same split."""
+    order = np.argsort(-np.asarray(cost, dtype=np.float64), kind="stable")
+    load = np.zeros(world)
+    bins = [[] for _ in range(world)]
+    for i in order:
+        r = int(np.argmin(load))
+        bins[r].append(int(i))
+        load[r] += max(float(cost[i]), 0.0) + 1e-9
+    return [np.asarray(sorted(b), dtype=np.int64) for b in bins]
 
 
 def shard_range(n: int, rank: int, world: int):

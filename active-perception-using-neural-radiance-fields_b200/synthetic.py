@@ -96,3 +96,63 @@ def pose_to_matrix(pose7):
     m[:3, :3] = quat_xyzw_to_matrix(pose7[3:])
     m[:3, 3] = pose7[:3]
     return m
+
+
+class TrainingSet:
+    """Synthetic posed rgb / depth / semantic images and the reference's training-batch sampler (SURVEY.md section
+    8(d)-4): `n_images` poses, W x H images with random rgb U8, depth U(0.5, 8) f32, labels randint(0, C) i64
+    (seed 4), all resident on `device`.  ``fetch(num_rays)`` mirrors Dataset.fetch_data + preprocess in training
+    mode (perception/data_proc/habitat_to_data.py:184-272): ONE random image per batch, `num_rays` random pixels of
+    it, pinhole OpenGL rays, random background colour."""
+
+    def __init__(self, n_images=40, width=320, height=240, focal=160.0, n_classes=29, seed=4, device="cpu"):
+        g = torch.Generator().manual_seed(seed)
+        self.width, self.height, self.size = width, height, n_images
+        self.device = torch.device(device)
+        self.images = torch.randint(0, 256, (n_images, height, width, 3), generator=g, dtype=torch.uint8).to(self.device)
+        self.depths = (torch.rand((n_images, height, width), generator=g) * 7.5 + 0.5).to(self.device)
+        self.semantics = torch.randint(0, n_classes, (n_images, height, width), generator=g).to(self.device)
+        poses = make_poses(n_images, seed=seed)
+        c2w = np.stack([pose_to_matrix(p)[:3] for p in poses]).astype(np.float32)
+        self.camtoworlds = torch.from_numpy(c2w).to(self.device)
+        self.K = torch.tensor([[focal, 0, width / 2.0], [0, focal, height / 2.0], [0, 0, 1]], device=self.device)
+        self.gen = torch.Generator(device=self.device).manual_seed(seed + 1)
+
+    def fetch_from_host(self, host, num_rays):
+        """The same batch drawn from HOST copies of the images (pinned memory -> device every step): the end-to-end
+        variant of the training benchmark."""
+        g = getattr(self, "_host_gen", None)
+        if g is None:
+            g = self._host_gen = torch.Generator().manual_seed(12345)
+        image_id = torch.randint(0, self.size, (1,), generator=g)
+        x = torch.randint(0, self.width, (num_rays,), generator=g)
+        y = torch.randint(0, self.height, (num_rays,), generator=g)
+        pix = host["images"][image_id, y, x].pin_memory().to(self.device, non_blocking=True)
+        dep = host["depths"][image_id, y, x].pin_memory().to(self.device, non_blocking=True)
+        sem = host["semantics"][image_id, y, x].pin_memory().to(self.device, non_blocking=True)
+        return self._batch(image_id.to(self.device), x.to(self.device), y.to(self.device), pix / 255.0, dep, sem)
+
+    def fetch(self, num_rays):
+        dev, g = self.device, self.gen
+        image_id = torch.randint(0, self.size, (1,), device=dev, generator=g)
+        x = torch.randint(0, self.width, (num_rays,), device=dev, generator=g)
+        y = torch.randint(0, self.height, (num_rays,), device=dev, generator=g)
+        rgb = self.images[image_id, y, x] / 255.0
+        dep = self.depths[image_id, y, x]
+        sem = self.semantics[image_id, y, x]
+        return self._batch(image_id, x, y, rgb, dep, sem)
+
+    def _batch(self, image_id, x, y, rgb, dep, sem):
+        from .render import Rays
+
+        dev, g = self.device, self.gen
+        num_rays = x.shape[0]
+        c2w = self.camtoworlds[image_id]
+        camera_dirs = torch.nn.functional.pad(torch.stack([(x - self.K[0, 2] + 0.5) / self.K[0, 0],
+                                                           (y - self.K[1, 2] + 0.5) / self.K[1, 1] * -1.0], dim=1),
+                                              (0, 1), value=-1.0)
+        directions = (camera_dirs[:, None, :] * c2w[:, :3, :3]).sum(dim=-1)
+        origins = torch.broadcast_to(c2w[:, :3, -1], directions.shape).contiguous()
+        viewdirs = directions / torch.linalg.norm(directions, dim=-1, keepdims=True)
+        return {"pixels": rgb.reshape(num_rays, 3), "dep": dep.reshape(num_rays), "sem": sem.reshape(num_rays),
+                "rays": Rays(origins=origins, viewdirs=viewdirs), "color_bkgd": torch.rand(3, device=dev, generator=g)}

@@ -16,22 +16,31 @@ from .nerfacc import DensityOccEvalFn
 from .render import Rays, render_image_with_occgrid_with_depth_guide
 
 
-def allreduce_gradients(module: torch.nn.Module, process_group=None) -> None:
-    """Average parameter gradients over the ranks: one flattened all-reduce per parameter tensor
-    (three large tensors here, so bucketing is already done by the tcnn-style flat layout)."""
+def allreduce_gradients(module: torch.nn.Module, process_group=None, contributed: bool = True) -> int:
+    """Sum parameter gradients over the ranks and divide by the number of ranks that CONTRIBUTED a batch (one
+    flattened all-reduce per parameter tensor: three large tensors here, so bucketing is already done by the
+    tcnn-style flat layout).  Every rank must call this every step, including a rank whose batch produced no
+    samples (it contributes zeros and ``contributed=False``): the skip decision is taken from the reduced count, so
+    the ranks stay in lock step.  Returns the number of contributing ranks."""
     import torch.distributed as dist
 
-    if not (dist.is_available() and dist.is_initialized()):
-        return
-    world = dist.get_world_size(process_group)
-    if world == 1:
-        return
     for p in module.parameters():
         if p.grad is None:
             p.grad = torch.zeros_like(p)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(process_group) == 1:
+        return 1 if contributed else 0
+    dev = next(module.parameters()).device
+    flag = torch.tensor([1.0 if contributed else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=process_group)
+    for p in module.parameters():
         if p.grad.numel():
             dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=process_group)
-            p.grad.div_(world)
+    n = int(flag.item())
+    if n > 1:
+        for p in module.parameters():
+            if p.grad.numel():
+                p.grad.div_(n)
+    return n
 
 
 def nerf_loss(rgb, depth, sem, batch: Dict[str, torch.Tensor]):
@@ -46,10 +55,11 @@ def nerf_loss(rgb, depth, sem, batch: Dict[str, torch.Tensor]):
 def training_step(radiance_field, estimator, optimizer, batch: Dict[str, torch.Tensor], step: int, *,
                   near_plane: float = 0.1, render_step_size: float = 1e-3, cone_angle: float = 0.004,
                   alpha_thre: float = 0.01, occ_thre: float = 1e-2, scheduler=None, process_group=None,
-                  update_occupancy: bool = True) -> Optional[Dict[str, float]]:
+                  update_occupancy: bool = True, read_loss: bool = True) -> Optional[Dict[str, float]]:
     """One optimisation step; ``batch`` holds ``rays`` (Rays of [n,3]), ``pixels [n,3]``, ``dep [n]``,
     ``sem [n] int64`` and ``color_bkgd [3]`` (habitat_to_data.py:205-272).  Returns the logged scalars,
-    or None when the step was skipped (no samples, or NaN gradients)."""
+    or None when the step was skipped (no samples on any rank, or NaN gradients).  ``read_loss=False`` leaves the
+    loss on the device (``"loss"`` is then a 0-d tensor): no host synchronisation for logging."""
     radiance_field.train()
     estimator.train()
     if update_occupancy:
@@ -64,19 +74,49 @@ def training_step(radiance_field, estimator, optimizer, batch: Dict[str, torch.T
         rgb, acc, depth, sem, n_samples = out
     else:
         (rgb, acc, depth, n_samples), sem = out, None
-    if n_samples == 0:  # pipeline.py:491
-        return None
-    loss = nerf_loss(rgb, depth, sem, batch)
     optimizer.zero_grad()
-    loss.backward()
-    allreduce_gradients(radiance_field, process_group)
-    for p in radiance_field.parameters():  # pipeline.py:520-529
-        if p.grad is None:
-            p.grad = torch.zeros_like(p)
-        if torch.isnan(p.grad).any():
-            optimizer.zero_grad()
-            return None
+    loss = None
+    if n_samples > 0:  # pipeline.py:491 skips an empty batch; under data parallelism the rank still joins the all-reduce
+        loss = nerf_loss(rgb, depth, sem, batch)
+        loss.backward()
+    if allreduce_gradients(radiance_field, process_group, contributed=n_samples > 0) == 0:
+        return None
+    # pipeline.py:520-529: skip the step when any gradient is NaN -- one fused reduction and ONE host read instead
+    # of a sync per parameter (the decision is the same on every rank: it is taken after the all-reduce)
+    bad = torch.stack([torch.isnan(p.grad).any() for p in radiance_field.parameters() if p.grad.numel()]).any()
+    if bool(bad):
+        optimizer.zero_grad()
+        return None
     optimizer.step()
     if scheduler is not None:
         scheduler.step()
-    return {"loss": float(loss.detach()), "n_samples": int(n_samples)}
+    if loss is None:
+        return {"loss": float("nan"), "n_samples": 0}
+    return {"loss": float(loss.detach()) if read_loss else loss.detach(), "n_samples": int(n_samples)}
+
+
+class EnsembleTrainer:
+    """``nerf_training``'s inner loop over the ensemble (scripts/pipeline.py:403-532): every call of ``step``
+    trains each member-model once on its own freshly drawn ray batch."""
+
+    def __init__(self, fields, estimators, optimizers, *, near_plane=0.1, render_step_size=1e-3, cone_angle=0.004,
+                 alpha_thre=0.01, occ_thre=1e-2, schedulers=None, process_group=None):
+        self.fields, self.estimators, self.optimizers = list(fields), list(estimators), list(optimizers)
+        self.schedulers = list(schedulers) if schedulers is not None else [None] * len(self.fields)
+        self.opts = dict(near_plane=near_plane, render_step_size=render_step_size, cone_angle=cone_angle,
+                         alpha_thre=alpha_thre, occ_thre=occ_thre, process_group=process_group)
+        self.samples_seen = 0
+        self.steps_done = 0
+
+    def step(self, fetch, step: int, read_loss: bool = False):
+        """fetch() -> a training batch (called once per member, as the reference draws a new batch per model)."""
+        logs = []
+        for f, e, o, sch in zip(self.fields, self.estimators, self.optimizers, self.schedulers):
+            out = training_step(f, e, o, fetch(), step, scheduler=sch, read_loss=read_loss, **self.opts)
+            if out is not None:
+                self.samples_seen += out["n_samples"]
+                self.steps_done += 1
+                logs.append(out["loss"] if read_loss else None)
+            else:
+                logs.append(None)
+        return logs

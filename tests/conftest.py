@@ -18,10 +18,14 @@ def _built_library():
     and it travels to the GPU box -- but a fresh checkout has only sources: compile it once here (nvcc cross-compiles
     sm_100a without a GPU)."""
     pkg = os.path.join(ROOT, "active-perception-using-neural-radiance-fields_b200")
-    if not os.path.exists(os.path.join(pkg, "libapnerf.so")):
+    so = os.path.join(pkg, "libapnerf.so")
+    csrc = os.path.join(pkg, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in srcs)
+    if stale and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):  # incremental: seconds when little changed
         import subprocess
 
-        subprocess.run([sys.executable, os.path.join(pkg, "csrc", "build.py")], check=True, cwd=os.path.join(pkg, "csrc"))
+        subprocess.run([sys.executable, os.path.join(csrc, "build.py")], check=True, cwd=csrc)
     yield
 
 

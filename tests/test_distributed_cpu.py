@@ -114,3 +114,57 @@ def test_gradient_allreduce_world2_averages():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert np.allclose(wg, 1.5) and np.allclose(bg, 0.0)
+
+
+def _grad_worker_empty_rank(rank, world, port, ret):
+    """a rank whose batch produced no samples must still join the all-reduce (zeros,
+    contributed=False) and the mean must run over the contributing ranks only."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.training import allreduce_gradients
+
+    m = torch.nn.Linear(4, 3)
+    if rank == 0:
+        m.weight.grad = torch.full_like(m.weight, 3.0)
+        m.bias.grad = torch.full_like(m.bias, 5.0)
+    n = allreduce_gradients(m, contributed=(rank == 0))  # rank 1: no gradients at all
+    n_none = allreduce_gradients(torch.nn.Linear(2, 2), contributed=False)  # nobody contributed -> 0, zero grads
+    ret.put((rank, n, n_none, m.weight.grad.clone().numpy(), m.bias.grad.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_rank_without_samples():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker_empty_rank, args=(r, 2, port, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [ret.get(timeout=120) for _ in range(2)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, n, n_none, wg, bg in got:
+        assert n == 1 and n_none == 0
+        assert np.allclose(wg, 3.0) and np.allclose(bg, 5.0), (rank, wg, bg)  # sum over ranks / 1 contributing rank
+
+
+def test_lpt_assignment_is_balanced_and_deterministic():
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import lpt_assign
+
+    rng = np.random.default_rng(1)
+    cost = rng.uniform(0.7, 5.8, 256)  # the spread of per-view sample counts on the synthetic scene
+    bins = lpt_assign(cost, 8)
+    assert sorted(np.concatenate(bins).tolist()) == list(range(256))  # a partition
+    loads = np.array([cost[b].sum() for b in bins])
+    assert loads.max() / loads.mean() < 1.01
+    contiguous = np.array([cost[32 * r:32 * r + 32].sum() for r in range(8)])
+    assert loads.max() < contiguous.max()
+    again = lpt_assign(cost.copy(), 8)
+    assert all(np.array_equal(a, b) for a, b in zip(bins, again))
+    assert [len(b) for b in lpt_assign(np.ones(5), 2)] == [3, 2] and lpt_assign(np.zeros(0), 3)[0].size == 0
