@@ -26,24 +26,46 @@ _CTYPES = {
 }
 
 
+# element types a tensor may have when it is passed for a pointer parameter of the given C type (void* = untyped
+# buffers: fp16 tables / weight blobs / packed rows)
+_PTR_DTYPES = {
+    "float": (torch.float32,),
+    "double": (torch.float64,),
+    "int": (torch.int32,),
+    "int64_t": (torch.int64,),
+    "long long": (torch.int64,),
+    "uint8_t": (torch.uint8, torch.bool),
+    "uint32_t": (torch.int32, torch.uint32),
+    "void": None,
+    "char": None,
+}
+ARG_DTYPES = {}  # name -> per-argument tuple of allowed dtypes (None: not a typed pointer)
+
+
 def parse_header(path: str = HEADER_PATH):
-    """Return {name: (restype, [argtypes])} for every prototype declared in the header."""
+    """Return {name: (restype, [argtypes])} for every prototype declared in the header; fills ARG_DTYPES with the
+    element type each pointer parameter declares, so that a tensor of another dtype raises instead of being
+    reinterpreted (the reference's ``data_ptr<float>()`` raises too)."""
     src = open(path).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
     for m in re.finditer(r"(?:^|\n)\s*(const char\*|int|long long|void)\s+(apnerf_\w+)\s*\(([^;{]*?)\)\s*;", src):
         ret, name, args = m.group(1), m.group(2), m.group(3)
-        argtypes = []
+        argtypes, dtypes = [], []
         args = " ".join(args.split())
         if args and args != "void":
             for a in args.split(","):
                 a = a.strip()
                 if "*" in a:
                     argtypes.append(ctypes.c_void_p)
+                    base = a.split("*")[0].replace("const ", "").strip()
+                    dtypes.append(_PTR_DTYPES.get(base))
                 else:
                     ty = a.rsplit(" ", 1)[0].replace("const ", "").strip()
                     argtypes.append(_CTYPES[ty])
+                    dtypes.append(None)
+        ARG_DTYPES[name] = tuple(dtypes)
         restype = {"const char*": ctypes.c_char_p, "int": ctypes.c_int, "long long": ctypes.c_longlong,
                    "void": None}[ret]
         protos[name] = (restype, argtypes)
@@ -88,12 +110,13 @@ class _Lib:
         self._load()
         fn = getattr(self._dll, name)
         conv = []
-        for a in args:
+        for i, a in enumerate(args):
             if isinstance(a, torch.Tensor):
                 if not a.is_cuda:
                     raise RuntimeError(f"{name}: expected a CUDA tensor, got {a.device}")
                 if not a.is_contiguous():
                     raise RuntimeError(f"{name}: tensor arguments must be contiguous")
+                _check_dtype(name, i, a)
                 conv.append(ctypes.c_void_p(a.data_ptr()))
             elif a is None:
                 conv.append(ctypes.c_void_p(0))
@@ -119,10 +142,11 @@ class PreparedCall:
         self.name = name
         self.fn = getattr(LIB._dll, name)
         conv, keep = [], []
-        for a in args:
+        for i, a in enumerate(args):
             if isinstance(a, torch.Tensor):
                 if not a.is_cuda or not a.is_contiguous():
                     raise RuntimeError(f"{name}: tensor arguments must be contiguous CUDA tensors")
+                _check_dtype(name, i, a)
                 keep.append(a)
                 conv.append(ctypes.c_void_p(a.data_ptr()))
             elif a is None:
@@ -143,6 +167,14 @@ class PreparedCall:
         rc = self.fn(*self.args)
         if rc != 0:
             raise RuntimeError(f"{self.name} failed (code {rc}): {LIB.last_error()}")
+
+
+def _check_dtype(name, i, t):
+    allowed = ARG_DTYPES.get(name, ())
+    allowed = allowed[i] if i < len(allowed) else None
+    if allowed is not None and t.dtype not in allowed:
+        raise RuntimeError(f"{name}: argument {i} must be a tensor of dtype {' / '.join(str(d) for d in allowed)}, "
+                           f"got {t.dtype} (the kernels read raw device pointers; cast at the call site)")
 
 
 CALL_HOOK = None

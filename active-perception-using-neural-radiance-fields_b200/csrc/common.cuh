@@ -38,15 +38,18 @@ void apnerf_set_error_msg(const char* msg);
     }                                                     \
   } while (0)
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs).
 static inline int apnerf_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 static inline int ceil_div_i(long long a, long long b) { return (int)((a + b - 1) / b); }

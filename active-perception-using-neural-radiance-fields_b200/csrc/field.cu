@@ -4,6 +4,7 @@
 // NGPRadianceField (perception/models/radiance_fields/ngp.py:107-238).
 #include "field_kernel.cuh"
 #include "field_bwd_kernel.cuh"
+#include "field_wgrad_kernel.cuh"
 
 namespace apnerf {
 
@@ -242,10 +243,12 @@ APNERF_API int apnerf_field_backward(long long n, const float* d_dens, const flo
   APNERF_REQUIRE(act_stride >= 128 && act_stride % 8 == 0 && g_stride >= 128 && g_stride % 8 == 0,
                  "field_backward: row strides must be multiples of 8, >= 128");
   APNERF_REQUIRE(n_sem >= 0 && n_sem <= SEM_OUT && loss_scale > 0.f, "field_backward: bad n_sem / loss_scale");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_done = 0ull;  // bit d: opted in on device d (function attributes are per device)
+  int dev = 0;
+  APNERF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((attr_done >> dev) & 1ull)) {
     APNERF_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    attr_set = true;
+    if (dev < 64) attr_done |= 1ull << dev;
   }
   FieldBwdIO io;
   io.n = n, io.d_dens = d_dens, io.d_rgb = d_rgb, io.d_sem = d_sem, io.n_sem = d_sem ? n_sem : 0;
@@ -259,6 +262,31 @@ APNERF_API int apnerf_field_backward(long long n, const float* d_dens, const flo
   const long long cap = 2LL * apnerf_num_sms();  // two 112 KB CTAs fit one SM: one's epilogue hides the other's MMAs
   field_backward_kernel<<<(int)(tiles < cap ? tiles : cap), BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(io);
   APNERF_CHECK_LAUNCH("field_backward_kernel");
+  return 0;
+}
+
+// Weight gradients of the three MLPs (csrc/field_wgrad_kernel.cuh): d_* += G^T . X / loss_scale for the nine layers.
+// G [n_pad, 576], X [n_pad, 624] fp16 row-major with rows >= n zero and n_pad a multiple of 32; d_base / d_head /
+// d_sem: the flat fp32 gradients of [W1|W2|W3], [WH1|WH2|WH3], [WS1|WS2|WS3] (d_sem may be NULL).
+APNERF_API int apnerf_field_wgrad(long long n, const void* G, const void* X, float loss_scale, float* d_base,
+                                  float* d_head, float* d_sem, int sem_out_rows, void* stream) {
+  if (n == 0) return 0;
+  APNERF_REQUIRE(G && X && d_base && d_head && loss_scale > 0.f, "field_wgrad: null buffer / bad loss scale");
+  APNERF_REQUIRE(sem_out_rows == 16 || sem_out_rows == 32 || d_sem == nullptr, "field_wgrad: sem_out_rows must be 16 or 32");
+  static unsigned long long attr_done = 0ull;
+  int dev = 0;
+  APNERF_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((attr_done >> dev) & 1ull)) {
+    APNERF_CUDA(cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    if (dev < 64) attr_done |= 1ull << dev;
+  }
+  WgradIO io;
+  io.n = n, io.G = (const __half*)G, io.X = (const __half*)X, io.scale = 1.0f / loss_scale;
+  io.d_base = d_base, io.d_head = d_head, io.d_sem = d_sem, io.sem_out_rows = sem_out_rows;
+  const long long stages = (n + WG_STAGE_ROWS - 1) / WG_STAGE_ROWS;
+  const int sms = apnerf_num_sms();
+  field_wgrad_kernel<<<(int)(stages < sms ? stages : sms), WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(io);
+  APNERF_CHECK_LAUNCH("field_wgrad_kernel");
   return 0;
 }
 

@@ -92,8 +92,8 @@ struct FieldIO {
   float* sem;
   long long sem_row, sem_ch;
   __half* feat;                 // optional [n, 15] geo features (query_density(return_feat=True))
-  uint4* packed;                // optional [n][5] x 16 B rows of 40 fp16: raw network outputs for the fused
-                                // renderer {density logit (-inf outside the aabb), rgb logits x3, sigma fp32, pad, 32 sem logits}
+  uint4* packed;                // optional [n][5] x 16 B rows for the renderer's compositor:
+                                // {sigma, r, g, b as fp32 (activated) | 32 semantic logits fp16}
   int n_sem;                    // number of semantic classes actually written (<= 32), 0 = none
   int density_only;             // stop after the base MLP
   // --- fused compositing (device-driven renderer): when `state` is set, the epilogue composites each
@@ -253,13 +253,13 @@ __device__ __forceinline__ void composite_tile(const FieldIO& io, const Composit
   for (int q = 0; q < 5; ++q) *reinterpret_cast<uint4*>(sm.rowbuf + q * (TILE_M * 16) + row * 16) = my_row[q];
   sm.cbuf[row] = (uint8_t)code;
   {
-    const __half* h0 = reinterpret_cast<const __half*>(&my_row[0]);
-    const float sdt = __fmul_rn(__uint_as_float(my_row[0].z), __fsub_rn(t1, t0));
+    const float sdt = __fmul_rn(__uint_as_float(my_row[0].x), __fsub_rn(t1, t0));
     sm.fbuf[0 * TILE_M + row] = sdt;
     sm.fbuf[1 * TILE_M + row] = __fsub_rn(1.0f, expf(-sdt));
     sm.fbuf[2 * TILE_M + row] = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sm.fbuf[(3 + c) * TILE_M + row] = 1.0f / (1.0f + expf(-__half2float(h0[1 + c])));
+    sm.fbuf[3 * TILE_M + row] = __uint_as_float(my_row[0].y);
+    sm.fbuf[4 * TILE_M + row] = __uint_as_float(my_row[0].z);
+    sm.fbuf[5 * TILE_M + row] = __uint_as_float(my_row[0].w);
   }
   chain_bar_sync(chain);
   const int k = leader ? code : (in_ray ? (int)sm.cbuf[row - j] : 0);
@@ -632,13 +632,15 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       ptx::tc_fence_before();
       ptx::mbar_arrive(my_epi);  // outputs are in registers: the next tile's layer 1 may overwrite TMEM
       if (FUSED || (valid && (XROWS || io.packed))) {
+        // row = {sigma, r, g, b as fp32 | 32 semantic logits fp16}: the activations run HERE, sample-parallel with all
+        // 128 lanes busy -- sigma = exp(fp16 logit - 1) * selector (ngp.py:79,191-193), rgb = sigmoid(fp16 logit)
+        // (ngp.py:211-212) -- so the ray-parallel compositor, whose lanes diverge, is left with two exps per sample
         __align__(16) __half row_h[40];
-        row_h[0] = dens_logit;
+        float* row_f = reinterpret_cast<float*>(row_h);
+        row_f[0] = expf(__fsub_rn(__half2float(dens_logit), 1.0f));
 #pragma unroll
-        for (int c = 0; c < 3; ++c) row_h[1 + c] = __float2half_rn(__uint_as_float(oh[c]));
-        // halves 4-5 carry sigma = exp(logit - 1) * selector as fp32 so the compositor needs no exp for it
-        reinterpret_cast<float*>(row_h)[2] = expf(__fsub_rn(__half2float(dens_logit), 1.0f));
-        row_h[6] = row_h[7] = __ushort_as_half((unsigned short)0);
+        for (int c = 0; c < 3; ++c)
+          row_f[1 + c] = 1.0f / (1.0f + expf(-__half2float(__float2half_rn(__uint_as_float(oh[c])))));
 #pragma unroll
         for (int c = 0; c < 32; ++c) row_h[8 + c] = __float2half_rn(__uint_as_float(os[c]));
         if (FUSED) {

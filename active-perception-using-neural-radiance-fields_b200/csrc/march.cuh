@@ -17,7 +17,15 @@ struct GridView {
   int n_grids;
   int rx, ry, rz;
   float skip_min_steps;  // use the closed-form skip only when more than this many steps are expected
+  const uint32_t* bits;  // optional: the same occupancy, one bit per cell (cell i = bit i & 31 of word i >> 5 of its level);
+                         // 8x less cache footprint than the bool bytes, which is what the serial per-cell walk waits on
 };
+
+__device__ __forceinline__ bool cell_occupied(const GridView& g, const uint8_t* __restrict__ lvl_bin,
+                                              const uint32_t* __restrict__ lvl_bits, int cid) {
+  if (lvl_bits) return (__ldg(lvl_bits + (cid >> 5)) >> (cid & 31)) & 1u;
+  return lvl_bin[cid] != 0;
+}
 
 __device__ __forceinline__ float calc_dt(float t, float cone, float dt_min) {
   // grid.cu:23-28 : clamp(t * cone, dt_min, 1e10) = fmaxf(dt_min, fminf(t * cone, 1e10))
@@ -48,6 +56,12 @@ __device__ __forceinline__ bool ray_aabb(const float o[3], const float inv[3], f
   return true;
 }
 
+
+// The reference's empty-space skip loop itself (grid.cu:157-161, 199-203), every add rounded to nearest.
+__device__ __forceinline__ float skip_loop(float t, float dt, float target) {
+  while (__fmaf_rn(dt, 0.5f, t) < target) t = __fadd_rn(t, dt);
+  return t;
+}
 
 // Exact closed form of the reference's empty-space skip loop (grid.cu:157-161, 199-203)
 //     while (fma(dt, 0.5, t) < target) t = t + dt;          // every add rounded to nearest
@@ -97,7 +111,10 @@ __device__ __forceinline__ float skip_to(float t, float dt, float target, float 
 // order; it returns nothing (counting is done here).  `limit` <= 0 means unlimited.
 // Returns the number of samples; `n_intervals` gets the number of interval edges
 // (#samples + #runs) and `t_term` the terminate plane (grid.cu:274-280).
-template <class Sink>
+// FAST (the renderer's instantiation): step_size > 0 is known and the closed-form skip is compiled out (an empty
+// 0.1 m cell is at most ~100 steps; the closed form only pays for pathological skips, see skip_to), which removes
+// eight instructions of uniform tests from every cell visit.
+template <bool FAST = false, class Sink>
 __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], const float d[3],
                                          float near_plane, float far_plane,
                                          const uint8_t* __restrict__ hits,        // [n_grids] of this ray
@@ -127,20 +144,28 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
     const float this_tmax = fminf(t_sorted[i + 1], far_plane);
     if (this_tmin >= this_tmax) continue;
 
+    const bool free_step = !FAST && step_size <= 0.0f;
     if (!continuous) {  // grid.cu:153-163
-      if (step_size <= 0.0f) {
+      if (free_step) {
         t_last = this_tmin;
       } else {
         const float dt = calc_dt(t_last, cone_angle, step_size);
-        t_last = skip_to(t_last, dt, this_tmin, g.skip_min_steps);
+        t_last = FAST ? skip_loop(t_last, dt, this_tmin) : skip_to(t_last, dt, this_tmin, g.skip_min_steps);
       }
     }
 
     // setup_traversal, include/utils_grid.cuh:58-114
     const float* __restrict__ ab = g.aabbs + level * 6;
     const int resv[3] = {g.rx, g.ry, g.rz};
+    const int cell_stride[3] = {g.ry * g.rz, g.rz, 1};
+    // Per-axis DDA state, all kept in registers: distance to the next boundary, its increment, the cell-id increment and
+    // a countdown to the "stepped onto the overflow cell" exit.  The reference tests cur[a] == overflow_index[a] after
+    // cur[a] += step[a] (utils_grid.cuh:131-141); with diff = overflow - cur that is `diff -= step; diff == 0`, and
+    // cnt = diff * step counts the same thing down by one per step (step = 0: the reference exits the first time the
+    // axis is chosen, cnt = 1 does the same; diff * step <= 0 never reaches zero in either form).
     float tdist[3], delta[3];
-    int cur[3], stp[3], ovf[3];
+    int idstep[3], cnt[3];
+    int cid = 0;
     const float ts = __fadd_rn(this_tmin, eps), te = __fsub_rn(this_tmax, eps);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -149,39 +174,47 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
       const float voxel = __fdiv_rn(ext, fres);
       const float ray_start = __fmaf_rn(d[a], ts, o[a]);
       const float ray_end = __fmaf_rn(d[a], te, o[a]);
-      cur[a] = clampi(__float2int_rz(__fmul_rn(__fdiv_rn(__fsub_rn(ray_start, ab[a]), ext), fres)), 0, resv[a] - 1);
+      const int cur = clampi(__float2int_rz(__fmul_rn(__fdiv_rn(__fsub_rn(ray_start, ab[a]), ext), fres)), 0, resv[a] - 1);
       const int fin = clampi(__float2int_rz(__fmul_rn(__fdiv_rn(__fsub_rn(ray_end, ab[a]), ext), fres)), 0, resv[a] - 1);
-      const int start_index = cur[a] + (d[a] > 0.0f ? 1 : 0);
+      const int start_index = cur + (d[a] > 0.0f ? 1 : 0);
       const float inner = __fmaf_rn((float)start_index, voxel, -ray_start);
       const float tm = __fmaf_rn(__fadd_rn(ab[a], inner), inv[a], this_tmin);
-      const float sf = (d[a] == 0.0f) ? 0.0f : (d[a] > 0.0f ? 1.0f : -1.0f);
+      const int stp = (d[a] == 0.0f) ? 0 : (d[a] > 0.0f ? 1 : -1);
+      const float sf = (float)stp;
       tdist[a] = (d[a] == 0.0f) ? this_tmax : tm;
-      stp[a] = (int)sf;
       delta[a] = (d[a] == 0.0f) ? this_tmax : __fmul_rn(__fmul_rn(voxel, inv[a]), sf);
-      ovf[a] = fin + stp[a];
+      idstep[a] = stp * cell_stride[a];
+      cnt[a] = stp == 0 ? 1 : (fin + stp - cur) * stp;
+      cid += cur * cell_stride[a];
     }
-    // The cell id is kept incrementally (cur[] itself is only needed for the start cell) and the
-    // "stepped onto the overflow cell" test cur[a] == ovf[a] (utils_grid.cuh:131-141) as a per-axis
-    // difference that a step reduces by stp[a]: the same predicate, fewer instructions per cell.
-    const uint8_t* __restrict__ lvl_bin = g.binaries + (int64_t)level * g.rx * g.ry * g.rz;
-    int cid = cur[0] * g.ry * g.rz + cur[1] * g.rz + cur[2];
-    const int idstep[3] = {stp[0] * g.ry * g.rz, stp[1] * g.rz, stp[2]};
-    int diff[3] = {ovf[0] - cur[0], ovf[1] - cur[1], ovf[2] - cur[2]};
+    const int n_cells = g.rx * g.ry * g.rz;
+    const uint8_t* __restrict__ lvl_bin = g.binaries + (int64_t)level * n_cells;
+    const uint32_t* __restrict__ lvl_bits = g.bits ? g.bits + (int64_t)level * ((n_cells + 31) >> 5) : nullptr;
 
+    // The walk over the cells is a serial chain whose longest link is the occupancy load, so the NEXT cell's occupancy
+    // is fetched before the current cell is processed: which cell comes next depends only on tdist, not on the samples.
+    bool occ = cell_occupied(g, lvl_bin, lvl_bits, cid);
     while (limit <= 0 || n_samples < limit) {  // grid.cu:184
       const float t_traverse = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
-      if (!lvl_bin[cid]) {
-        if (step_size <= 0.0f) {
+      // single_traversal, include/utils_grid.cuh:116-142: step along the axis with the nearest boundary
+      const bool m0 = (tdist[0] < tdist[1]) && (tdist[0] < tdist[2]);
+      const bool m1 = !m0 && (tdist[1] < tdist[2]);
+      const int next_cid = cid + (m0 ? idstep[0] : (m1 ? idstep[1] : idstep[2]));
+      const int left = (m0 ? cnt[0] : (m1 ? cnt[1] : cnt[2])) - 1;
+      bool occ_next = false;
+      if (left != 0 && (unsigned)next_cid < (unsigned)n_cells) occ_next = cell_occupied(g, lvl_bin, lvl_bits, next_cid);
+      if (!occ) {
+        if (free_step) {
           t_last = t_traverse;
         } else {
           const float dt = calc_dt(t_last, cone_angle, step_size);
-          t_last = skip_to(t_last, dt, t_traverse, g.skip_min_steps);
+          t_last = FAST ? skip_loop(t_last, dt, t_traverse) : skip_to(t_last, dt, t_traverse, g.skip_min_steps);
         }
         continuous = false;
       } else {
         while (limit <= 0 || n_samples < limit) {  // grid.cu:208
           float t_next;
-          if (step_size <= 0.0f) {
+          if (free_step) {
             t_next = t_traverse;
           } else {
             const float dt = calc_dt(t_last, cone_angle, step_size);
@@ -196,15 +229,12 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
           if (t_next >= t_traverse) break;
         }
       }
-      // single_traversal, include/utils_grid.cuh:116-142: step along the axis with the nearest boundary.
-      // Three tiny predicated bodies instead of a three-way branch (the lanes of a warp pick different axes).
-      const bool m0 = (tdist[0] < tdist[1]) && (tdist[0] < tdist[2]);
-      const bool m1 = !m0 && (tdist[1] < tdist[2]);
-      const bool m2 = !m0 && !m1;
-      if (m0) { tdist[0] = __fadd_rn(tdist[0], delta[0]); diff[0] -= stp[0]; cid += idstep[0]; }
-      if (m1) { tdist[1] = __fadd_rn(tdist[1], delta[1]); diff[1] -= stp[1]; cid += idstep[1]; }
-      if (m2) { tdist[2] = __fadd_rn(tdist[2], delta[2]); diff[2] -= stp[2]; cid += idstep[2]; }
-      if ((m0 ? diff[0] : (m1 ? diff[1] : diff[2])) == 0) break;
+      if (m0) { tdist[0] = __fadd_rn(tdist[0], delta[0]); cnt[0] = left; }
+      else if (m1) { tdist[1] = __fadd_rn(tdist[1], delta[1]); cnt[1] = left; }
+      else { tdist[2] = __fadd_rn(tdist[2], delta[2]); cnt[2] = left; }
+      cid = next_cid;
+      occ = occ_next;
+      if (left == 0) break;
     }
   }
   t_term = t_last;

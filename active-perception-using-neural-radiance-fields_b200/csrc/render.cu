@@ -79,6 +79,20 @@ __global__ void __launch_bounds__(256) generate_rays_kernel(int n_views, const f
   }
 }
 
+// occupancy bools -> one bit per cell (word w, bit b = cell 32 w + b): the marcher's copy of the grid
+__global__ void __launch_bounds__(256) pack_occupancy_kernel(int n_cells, const uint8_t* __restrict__ binaries,
+                                                             uint32_t* __restrict__ bits) {
+  const int n_words = (n_cells + 31) >> 5;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += blockDim.x * gridDim.x) {
+    uint32_t v = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int c = 32 * w + b;
+      if (c < n_cells && binaries[c]) v |= 1u << b;
+    }
+    bits[w] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) render_init_kernel(int n_rays, int rays_per_call, const float* __restrict__ rays_o,
                                                           const float* __restrict__ rays_d, GridView g,
                                                           float near_plane, int n_state, float* __restrict__ state,
@@ -147,6 +161,7 @@ struct LocalSink {
 // One thread per live ray: march up to n samples from the ray's previous terminate plane and
 // append them to the compact per-iteration sample list (warp-aggregated reservation keeps the
 // samples of neighbouring rays adjacent, which is what gives the hash-grid gather its locality).
+template <bool FAST>
 __global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counters_in, int rays_per_call,
                                                            const int* __restrict__ alive, const int* __restrict__ n_samp,
                                                            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counter
         LocalSink sink{ts, te};
         int n_iv;
         float t_term;
-        k = march_ray(g, o, d, near[ray], far_plane, &h, tsorted, nullptr, step_size, cone_angle, n, sink, n_iv, t_term);
+        k = march_ray<FAST>(g, o, d, near[ray], far_plane, &h, tsorted, nullptr, step_size, cone_angle, n, sink, n_iv, t_term);
         near[ray] = t_term;  // utils.py:1002
       }
     }
@@ -215,6 +230,7 @@ __global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counter
 //   s_ray [row]  ray id or -1        s_cnt [row]  k at a ray's first row, 0x80 | j at its j-th row, 0 = padding
 // counters[2] = rows reserved this iteration (a multiple of 128).  keep_flag[ray] is cleared for
 // every live ray here and set by the fused compositor for the rays that stay live.
+template <bool FAST>
 __global__ void __launch_bounds__(256) render_march_tiles_kernel(
     const int* counters_in, int rays_per_call, const int* __restrict__ alive, const int* __restrict__ n_samp,
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, GridView g, const float* __restrict__ t_min,
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(256) render_march_tiles_kernel(
         LocalSink sink{ts, te};
         int n_iv;
         float t_term;
-        k = march_ray(g, o, d, near[ray], far_plane, &h, tsorted, nullptr, step_size, cone_angle, n, sink, n_iv, t_term);
+        k = march_ray<FAST>(g, o, d, near[ray], far_plane, &h, tsorted, nullptr, step_size, cone_angle, n, sink, n_iv, t_term);
         near[ray] = t_term;  // utils.py:1002
       }
     }
@@ -391,7 +407,7 @@ __global__ void __launch_bounds__(CMP_T) render_compact_kernel(const int* counte
 // array and the 32 semantic accumulators are processed 16 at a time, which lets the kernel run at 64
 // registers (8 CTAs of 128 threads per SM instead of 3 at 168): ncu shows it memory-latency bound (long
 // scoreboard 12 of 16 stall cycles per issue), so resident warps are what it needs; 48 registers measured slower.
-// Sample row (40 fp16): [density logit, r, g, b logits, sigma as fp32 (2 halves), 0, 0 | 32 sem logits].
+// Sample row (80 B): [sigma, r, g, b as fp32, already activated by the field kernel | 32 sem logits fp16].
 struct SampleTerms {
   float w, col[3], tmid;
   bool vis;
@@ -400,15 +416,13 @@ struct SampleTerms {
 __device__ __forceinline__ SampleTerms sample_terms(const uint4& r0, float t0, float t1, float esum, float prefix,
                                                     float alpha_thre, float& sdt_out) {
   SampleTerms o;
-  const __half* h0 = reinterpret_cast<const __half*>(&r0);
-  const float sigma = __uint_as_float(r0.z);  // exp(logit - 1) * selector, computed by the field kernel
+  const float sigma = __uint_as_float(r0.x);  // exp(logit - 1) * selector, computed by the field kernel
   const float sdt = __fmul_rn(sigma, __fsub_rn(t1, t0));
   const float alpha = __fsub_rn(1.0f, expf(-sdt));
   o.w = __fmul_rn(__fmul_rn(expf(-esum), prefix), alpha);
   o.vis = !(alpha_thre > 0.f && !(alpha >= alpha_thre));
   o.tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) o.col[c] = 1.0f / (1.0f + expf(-__half2float(h0[1 + c])));
+  o.col[0] = __uint_as_float(r0.y), o.col[1] = __uint_as_float(r0.z), o.col[2] = __uint_as_float(r0.w);
   sdt_out = sdt;
   return o;
 }
@@ -428,7 +442,8 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
   const size_t NR = (size_t)n_rays;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += blockDim.x * gridDim.x) {
     bool keep = false;
-    int ray = -1, call = -1, n_vis = 0;
+    int ray = -1, call = -1, n_vis = 0, sem_base = 0, sem_k = 0;
+    float wloc[MAX_ITER_SAMPLES];  // weight of sample j, or -1 when filtered by alpha_thre
     if (i < n_live) {
       ray = alive[i];
       call = ray / rays_per_call;
@@ -438,7 +453,6 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
       if (k > 0) {
         // pass 1: weights (kept in a small per-thread array: registers stay low, occupancy high),
         // rgb / opacity / depth
-        float wloc[MAX_ITER_SAMPLES];  // weight of sample j, or -1 when filtered by alpha_thre
         const float prefix = __fsub_rn(1.0f, opac);
         float rgb[3] = {st[0], st[NR], st[2 * NR]};
         float depth = st[ST_DEPTH * NR];
@@ -468,11 +482,10 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
             if (w < 0.f) continue;
             const int s = base + j;
             const uint4 r0 = __ldg(rows + (size_t)s * 5);
-            const __half* h0 = reinterpret_cast<const __half*>(&r0);
+            const float cols[3] = {__uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r0.w)};
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              const float col = 1.0f / (1.0f + expf(-__half2float(h0[1 + c])));
-              const float df = __fsub_rn(col, rgb[c]);
+              const float df = __fsub_rn(cols[c], rgb[c]);
               rv[c] = __fadd_rn(rv[c], __fmul_rn(w, __fmul_rn(df, df)));
             }
             const float dd = __fsub_rn(__fmul_rn(__fadd_rn(s_ts[s], s_te[s]), 0.5f), depth);
@@ -486,19 +499,35 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
         for (int c = 0; c < 3; ++c) st[c * NR] = rgb[c];
         st[ST_OPA * NR] = opac;
         st[ST_DEPTH * NR] = depth;
-        // pass 2: semantic logits, 16 channels (two 16-byte chunks of the row) at a time
+        }  // n_vis > 0
+      }
+      sem_base = base, sem_k = k;
+      const int n = n_samp[call];
+      keep = (n > 0) && (opac <= opc_thre) && (k == n) && (iter_samples[call] < max_samples);
+      if (ray_counts) ray_counts[ray] += k, ray_counts[NR + ray] += n_vis;  // parity instrumentation (tests)
+    }
+    // pass 2: semantic logits of the rays that composited something.  In the long tail of a render most live rays
+    // march through transparent space and only a few lanes of a warp have visible samples: looping over those rays
+    // with the WARP (8 lanes x 4 class channels per ray, four rays at a time) instead of letting each such lane run the
+    // 32-channel loop alone keeps the lanes busy there.  Dense warps (the first iterations) keep the per-thread form,
+    // 16 channels at a time, whose state accesses are coalesced across rays.  Same sums, same order, either way.
+    const bool has_sem = n_vis > 0 && n_sem > 0;
+    const unsigned sem_mask = __ballot_sync(0xffffffffu, has_sem);
+    if (__popc(sem_mask) > 16) {
+      if (has_sem) {
+        float* st = state + ray;
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
           if (16 * g >= n_sem) break;
           float acc[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) acc[c] = (16 * g + c < n_sem) ? st[(ST_SEM + 16 * g + c) * NR] : 0.f;
-          for (int j = 0; j < k; ++j) {
+          for (int j = 0; j < sem_k; ++j) {
             const float w = wloc[j];
             if (w < 0.f) continue;
             __align__(16) __half h[16];
-            reinterpret_cast<uint4*>(h)[0] = __ldg(rows + (size_t)(base + j) * 5 + 1 + 2 * g);
-            reinterpret_cast<uint4*>(h)[1] = __ldg(rows + (size_t)(base + j) * 5 + 2 + 2 * g);
+            reinterpret_cast<uint4*>(h)[0] = __ldg(rows + (size_t)(sem_base + j) * 5 + 1 + 2 * g);
+            reinterpret_cast<uint4*>(h)[1] = __ldg(rows + (size_t)(sem_base + j) * 5 + 2 + 2 * g);
 #pragma unroll
             for (int c = 0; c < 16; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w, __half2float(h[c])));
           }
@@ -506,11 +535,43 @@ __global__ void __launch_bounds__(128, 8) render_composite_kernel(
           for (int c = 0; c < 16; ++c)
             if (16 * g + c < n_sem) st[(ST_SEM + 16 * g + c) * NR] = acc[c];
         }
-        }  // n_vis > 0
       }
-      const int n = n_samp[call];
-      keep = (n > 0) && (opac <= opc_thre) && (k == n) && (iter_samples[call] < max_samples);
-      if (ray_counts) ray_counts[ray] += k, ray_counts[NR + ray] += n_vis;  // parity instrumentation (tests)
+    } else if (sem_mask) {
+      // four rays per warp step: 8 lanes x 4 channels each, so four rays' state / row loads are in flight together
+      const __half* rows_h = reinterpret_cast<const __half*>(rows);
+      const int grp = lane >> 3, sub = lane & 7, n_act = __popc(sem_mask);
+      for (int t0 = 0; t0 < n_act; t0 += 4) {
+        const bool on = t0 + grp < n_act;
+        const int owner = on ? (int)__fns(sem_mask, 0, t0 + grp + 1) : 0;  // lane of this group's ray
+        const int rb = __shfl_sync(0xffffffffu, ray, owner), bb = __shfl_sync(0xffffffffu, sem_base, owner);
+        const int kb_owner = __shfl_sync(0xffffffffu, sem_k, owner);
+        const int kb = on ? kb_owner : 0;
+        const int kmax = __reduce_max_sync(0xffffffffu, kb);
+        float* sp = state + (size_t)(ST_SEM + 4 * sub) * NR + (on ? rb : 0);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (on) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (4 * sub + c < n_sem) acc[c] = sp[(size_t)c * NR];
+        }
+        for (int j = 0; j < kmax; ++j) {
+          const float w = __shfl_sync(0xffffffffu, wloc[j], owner);
+          if (j < kb && w >= 0.f) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(rows_h + (size_t)(bb + j) * 40 + 8 + 4 * sub));
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(w, f01.x));
+            acc[1] = __fadd_rn(acc[1], __fmul_rn(w, f01.y));
+            acc[2] = __fadd_rn(acc[2], __fmul_rn(w, f23.x));
+            acc[3] = __fadd_rn(acc[3], __fmul_rn(w, f23.y));
+          }
+        }
+        if (on) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (4 * sub + c < n_sem) sp[(size_t)c * NR] = acc[c];
+        }
+      }
     }
     // compaction of the live list (order-preserving inside a warp) + per-call live counts
     const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -687,9 +748,14 @@ APNERF_API int apnerf_render_init(int n_rays, int rays_per_call, const float* ra
                                   int ry, int rz, const uint8_t* binaries, const float* aabbs, float near_plane,
                                   int n_state, float* state, float* t_min, float* t_max, uint8_t* hit, float* near,
                                   int* alive, int* n_alive_acc, int* iter_samples, int* total_samples, int n_calls,
-                                  int* counters, void* stream) {
+                                  int* counters, uint32_t* occ_bits, void* stream) {
   if (n_rays == 0) return 0;
   GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  if (occ_bits) {
+    const int n_cells = rx * ry * rz;
+    pack_occupancy_kernel<<<grid_for((n_cells + 31) / 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(n_cells, binaries, occ_bits);
+    APNERF_CHECK_LAUNCH("pack_occupancy_kernel");
+  }
   render_init_kernel<<<grid_for(n_rays, 256, 8), 256, 0, (cudaStream_t)stream>>>(
       n_rays, rays_per_call, rays_o, rays_d, g, near_plane, n_state, state, t_min, t_max, hit, near, alive,
       n_alive_acc, iter_samples, total_samples, n_calls, counters);
@@ -710,14 +776,16 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
                                    const uint8_t* binaries, const float* aabbs, const float* t_min, const float* t_max,
                                    const uint8_t* hit, float* near, float far_plane, float step_size, float cone_angle,
                                    int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
-                                   const float* field_aabb_host, void* s_x, int* counters, void* stream) {
+                                   const float* field_aabb_host, void* s_x, int* counters, const uint32_t* occ_bits,
+                                   void* stream) {
   if (max_live == 0) return 0;
-  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps(), occ_bits};
   FieldConst fc;
   for (int i = 0; i < 6; ++i) fc.aabb[i] = field_aabb_host[i];
   int mt, mc;
   apnerf_march_cfg(mt, mc);
-  render_march_kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
+  auto kernel = step_size > 0.0f ? render_march_kernel<true> : render_march_kernel<false>;
+  kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, fc, (float4*)s_x, counters);
   APNERF_CHECK_LAUNCH("render_march_kernel");
@@ -731,14 +799,15 @@ APNERF_API int apnerf_render_march_tiles(int max_live, int rays_per_call, const 
                                          const float* t_max, const uint8_t* hit, float* near, float far_plane,
                                          float step_size, float cone_angle, int* s_ray, uint8_t* s_cnt, float* s_ts,
                                          float* s_te, const float* field_aabb_host, void* s_x, uint8_t* keep_flag,
-                                         int s_cap, int* counters, void* stream) {
+                                         int s_cap, int* counters, const uint32_t* occ_bits, void* stream) {
   if (max_live == 0) return 0;
-  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps()};
+  GridView g{binaries, aabbs, 1, rx, ry, rz, apnerf_skip_min_steps(), occ_bits};
   FieldConst fc;
   for (int i = 0; i < 6; ++i) fc.aabb[i] = field_aabb_host[i];
   int mt, mc;
   apnerf_march_cfg(mt, mc);
-  render_march_tiles_kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
+  auto kernel = step_size > 0.0f ? render_march_tiles_kernel<true> : render_march_tiles_kernel<false>;
+  kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, s_ray, s_cnt, s_ts, s_te, fc, (float4*)s_x, keep_flag, s_cap, counters);
   APNERF_CHECK_LAUNCH("render_march_tiles_kernel");

@@ -19,7 +19,7 @@ def ray_aabb_intersect(rays_o: Tensor, rays_d: Tensor, aabbs: Tensor, near_plane
     assert rays_d.ndim == 2 and rays_d.shape[-1] == 3
     assert aabbs.ndim == 2 and aabbs.shape[-1] == 6
     require_cuda(rays_o, rays_d, aabbs)
-    rays_o, rays_d, aabbs = rays_o.contiguous(), rays_d.contiguous(), aabbs.contiguous()
+    rays_o, rays_d, aabbs = rays_o.float().contiguous(), rays_d.float().contiguous(), aabbs.float().contiguous()
     n, m = rays_o.shape[0], aabbs.shape[0]
     t_mins = torch.empty((n, m), device=rays_o.device, dtype=torch.float32)
     t_maxs = torch.empty((n, m), device=rays_o.device, dtype=torch.float32)
@@ -64,10 +64,11 @@ def traverse_grids(
         t_mins, t_maxs, hits = ray_aabb_intersect(rays_o, rays_d, aabbs)
         t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], dim=-1), dim=-1)
 
-    rays_o, rays_d = rays_o.contiguous(), rays_d.contiguous()
-    rays_mask, binaries, aabbs = rays_mask.contiguous(), binaries.contiguous(), aabbs.contiguous()
-    t_sorted, t_indices, hits = t_sorted.contiguous(), t_indices.contiguous(), hits.contiguous()
-    near_planes, far_planes = near_planes.contiguous(), far_planes.contiguous()
+    # the kernel reads raw float32 / int64 / 1-byte pointers: normalise dtypes here
+    rays_o, rays_d = rays_o.float().contiguous(), rays_d.float().contiguous()
+    rays_mask, binaries, aabbs = rays_mask.bool().contiguous(), binaries.bool().contiguous(), aabbs.float().contiguous()
+    t_sorted, t_indices, hits = t_sorted.float().contiguous(), t_indices.to(torch.int64).contiguous(), hits.bool().contiguous()
+    near_planes, far_planes = near_planes.float().contiguous(), far_planes.float().contiguous()
     dev = rays_o.device
     n_rays, n_grids = rays_o.shape[0], binaries.shape[0]
     rx, ry, rz = (int(s) for s in binaries.shape[1:])

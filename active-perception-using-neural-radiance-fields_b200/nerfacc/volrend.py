@@ -22,11 +22,12 @@ class _WeightsFromDensity(torch.autograd.Function):
     @staticmethod
     def forward(ctx, t_starts, t_ends, sigmas, packed_info, prefix_trans):
         require_cuda(t_starts, t_ends, sigmas, packed_info, prefix_trans)
-        t_starts, t_ends, sigmas = t_starts.contiguous(), t_ends.contiguous(), sigmas.contiguous()
-        chunk_starts = packed_info[:, 0].contiguous()
-        chunk_cnts = packed_info[:, 1].contiguous()
+        # the kernels read float32 / int64 device pointers: normalise here (an fp16 sigma from an autocast field, say)
+        t_starts, t_ends, sigmas = (t.float().contiguous() for t in (t_starts, t_ends, sigmas))
+        chunk_starts = packed_info[:, 0].to(torch.int64).contiguous()
+        chunk_cnts = packed_info[:, 1].to(torch.int64).contiguous()
         if prefix_trans is not None:
-            prefix_trans = prefix_trans.contiguous()
+            prefix_trans = prefix_trans.float().contiguous()
         weights = torch.empty_like(sigmas)
         trans = torch.empty_like(sigmas)
         alphas = torch.empty_like(sigmas)
@@ -59,11 +60,11 @@ class _Accumulate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, weights, values, ray_indices, n_rays):
         require_cuda(weights, values, ray_indices)
-        weights = weights.contiguous()
-        ray_indices = ray_indices.contiguous()
+        weights = weights.float().contiguous()
+        ray_indices = ray_indices.to(torch.int64).contiguous()
         D = 1 if values is None else values.shape[-1]
         if values is not None:
-            values = values.contiguous()
+            values = values.float().contiguous()
         outputs = torch.zeros((n_rays, D), device=weights.device, dtype=weights.dtype)
         if weights.numel():
             with torch.cuda.device(weights.device):
@@ -182,8 +183,10 @@ def accumulate_along_rays_(weights: Tensor, values: Optional[Tensor] = None, ray
         require_cuda(weights, values, ray_indices, outputs)
         if weights.numel():
             with torch.cuda.device(weights.device):
-                call("apnerf_accumulate_along_rays", weights.numel(), D, weights.detach().contiguous(),
-                     None if values is None else values.detach().contiguous(), ray_indices.contiguous(), outputs)
+                assert outputs.dtype == torch.float32, "outputs must be float32"
+                call("apnerf_accumulate_along_rays", weights.numel(), D, weights.detach().float().contiguous(),
+                     None if values is None else values.detach().float().contiguous(),
+                     ray_indices.to(torch.int64).contiguous(), outputs)
     else:
         src = weights[..., None] if values is None else weights[..., None] * values
         outputs.add_(src.sum(dim=-2))

@@ -9,7 +9,7 @@ Parameter layout (tcnn-compatible, flat fp32, so reference checkpoints load):
   direction_encoding.params = []  (SH has no parameters; kept so every named parameter exists)
 All matrices are row-major [out, in], no biases.
 """
-from typing import Callable, List, Union
+from typing import Optional, Callable, List, Union
 
 import numpy as np
 import torch
@@ -124,6 +124,22 @@ LOSS_SCALE = 128.0  # tcnn's default loss scale for fp16 networks (SURVEY.md App
 WGRAD_CHUNK = 32768
 
 
+WGRAD_LIBRARY_GEMM = False  # True: the round-1 path (one torch.bmm), kept as the on-GPU cross-check of the kernel
+
+
+def _wgrad_library(field, G, X, base_grad, head_grad, sem_grad):
+    """dW through ONE library GEMM G^T . X (fp16 operands, fp32 accumulation), reduced over fixed-size chunks."""
+    chunks = X.shape[0] // WGRAD_CHUNK
+    GX = torch.bmm(G.view(chunks, WGRAD_CHUNK, _G_WIDTH).transpose(1, 2), X.view(chunks, WGRAD_CHUNK, _X_WIDTH),
+                   out_dtype=torch.float32).sum(0) / LOSS_SCALE
+    dW = [GX[_G_COLS[g][0]:_G_COLS[g][1], _X_COLS[x][0]:_X_COLS[x][1]].reshape(-1) for g, x in _WGRAD_BLOCKS]
+    base_grad[: field._n_base_w] += torch.cat(dW[0:3])
+    head_grad += torch.cat(dW[3:6])
+    if sem_grad is not None:
+        f = field._sem_dims_flat[2]
+        sem_grad += torch.cat(dW[6:8] + [dW[8][: f[0] * f[1]]])
+
+
 def _padded_rows(n: int) -> int:
     return max(1, (n + WGRAD_CHUNK - 1) // WGRAD_CHUNK) * WGRAD_CHUNK
 
@@ -225,14 +241,17 @@ class _FusedMLPs(torch.autograd.Function):
                 call("apnerf_hashgrid_encode_bwd", n, x01, field.n_levels,
                      field._meta.ctypes.data_as(ctypes.c_void_p),
                      d_enc[:, : field.n_levels * 4].contiguous(), d_table)
-        # all weight gradients: G^T . X reduced over the samples in fixed-size chunks (see WGRAD_CHUNK)
-        chunks = X.shape[0] // WGRAD_CHUNK
-        GX = torch.bmm(G.view(chunks, WGRAD_CHUNK, _G_WIDTH).transpose(1, 2), X.view(chunks, WGRAD_CHUNK, _X_WIDTH),
-                       out_dtype=torch.float32).sum(0) / LOSS_SCALE
-        dW = [GX[_G_COLS[g][0]:_G_COLS[g][1], _X_COLS[x][0]:_X_COLS[x][1]].reshape(-1) for g, x in _WGRAD_BLOCKS]
-        base_grad[: field._n_base_w] = torch.cat(dW[0:3])
-        head_grad = torch.cat(dW[3:6])
-        sem_grad = torch.cat(dW[6:9]) if C > 0 else None
+        # all nine weight gradients dW = G^T . X / LOSS_SCALE: tcgen05 split-K kernel, accumulators in TMEM
+        # (csrc/field_wgrad_kernel.cuh); adds straight into the flat fp32 gradient vectors
+        head_grad = torch.zeros(sum(a * b for a, b in field._head_dims), device=dev, dtype=torch.float32)
+        sem_grad = torch.zeros(sum(a * b for a, b in field._sem_dims_flat), device=dev, dtype=torch.float32) if C > 0 else None
+        if n:
+            with torch.cuda.device(dev):
+                if WGRAD_LIBRARY_GEMM:
+                    _wgrad_library(field, G, X, base_grad, head_grad, sem_grad)
+                else:
+                    call("apnerf_field_wgrad", n, G, X, float(LOSS_SCALE), base_grad, head_grad, sem_grad,
+                         field._sem_dims_flat[2][0] if C > 0 else 32)
         # the zero-length SH parameter vector gets a (zero-length) gradient too: the reference's NaN guard calls
         # torch.isnan(param.grad) on EVERY named parameter (scripts/pipeline.py:521-524)
         dir_grad = torch.zeros(0, device=dev, dtype=torch.float32)
@@ -249,7 +268,7 @@ class NGPRadianceField(torch.nn.Module):
         use_viewdirs: bool = True,
         neurons: int = 128,
         layers: int = 4,
-        density_activation: Callable = lambda x: trunc_exp(x - 1),
+        density_activation: Optional[Callable] = None,
         unbounded: bool = False,
         base_resolution: int = 16,
         max_resolution: int = 4096,
@@ -264,7 +283,13 @@ class NGPRadianceField(torch.nn.Module):
         self.register_buffer("aabb", aabb)
         self.num_dim = num_dim
         self.use_viewdirs = use_viewdirs
-        self.density_activation = density_activation
+        # the sm_100a kernels (renderer, occupancy update, query_density) hard-code the reference's default
+        # density activation trunc_exp(x - 1) (ngp.py:79): another callable would train with one density and render
+        # with another, so it is refused instead of silently ignored
+        if density_activation is not None:
+            raise NotImplementedError("density_activation other than the default trunc_exp(x - 1) is not supported "
+                                      "by the fused sm_100a kernels")
+        self.density_activation = lambda x: trunc_exp(x - 1)
         self.unbounded = unbounded
         self.base_resolution = base_resolution
         self.max_resolution = max_resolution
@@ -287,14 +312,16 @@ class NGPRadianceField(torch.nn.Module):
         enc_dim = 64  # the kernel's A tile is 64 wide; levels beyond n_levels read as zeros
         self._base_dims = [(neurons, enc_dim)] + [(neurons, neurons)] * (layers - 1) + [(16, neurons)]
         self._head_dims = [(neurons // 2, 32), (neurons // 2, neurons // 2), (16, neurons // 2)]
-        self._sem_dims = [(neurons // 2, 16), (neurons // 2, neurons // 2), (32, neurons // 2)]
+        self._sem_dims = [(neurons // 2, 16), (neurons // 2, neurons // 2), (32, neurons // 2)]  # kernel image
+        # tcnn pads the output width to a multiple of 16: the flat ``mlp_sem.params`` has 16 output rows for C <= 16
+        self._sem_dims_flat = self._sem_dims[:2] + [(_pad16(max(1, num_semantic_classes)), neurons // 2)]
         n_base_w = sum(a * b for a, b in self._base_dims)
 
         self.direction_encoding = _FlatParams(0, n_output_dims=16)
         self.mlp_base = _FlatParams(n_base_w + self._n_entries * 4, n_output_dims=1 + geo_feat_dim)
         self.mlp_head = _FlatParams(sum(a * b for a, b in self._head_dims), n_output_dims=3)
         if num_semantic_classes > 0:
-            self.mlp_sem = _FlatParams(sum(a * b for a, b in self._sem_dims), n_output_dims=num_semantic_classes)
+            self.mlp_sem = _FlatParams(sum(a * b for a, b in self._sem_dims_flat), n_output_dims=num_semantic_classes)
         self._n_base_w = n_base_w
         self._cache = None
         self._cache_key = None
@@ -307,7 +334,7 @@ class NGPRadianceField(torch.nn.Module):
         self.mlp_base.params[o:].uniform_(-grid_range, grid_range, generator=generator)
         _xavier_(self.mlp_head.params, self._head_dims, generator)
         if self.num_semantic_classes > 0:
-            _xavier_(self.mlp_sem.params, self._sem_dims, generator)
+            _xavier_(self.mlp_sem.params, self._sem_dims_flat, generator)
 
     # -- fp16 inference image of the parameters (rebuilt when a parameter changes) --
     def _packed(self):
@@ -320,16 +347,19 @@ class NGPRadianceField(torch.nn.Module):
         with torch.no_grad():
             dev = self.mlp_base.params.device
 
-            def mats(flat, dims):
+            def mats(flat, dims, rows=None):
                 out, o = [], 0
-                for n_out, n_in in dims:
-                    out.append(_umma_pack(flat[o:o + n_out * n_in].reshape(n_out, n_in).to(torch.float16)))
+                for i, (n_out, n_in) in enumerate(dims):
+                    w = flat[o:o + n_out * n_in].reshape(n_out, n_in).to(torch.float16)
+                    if rows is not None and rows[i] > n_out:  # zero rows up to the kernel's padded output width
+                        w = torch.cat([w, w.new_zeros((rows[i] - n_out, n_in))])
+                    out.append(_umma_pack(w))
                     o += n_out * n_in
                 return out
 
             blobs = mats(self.mlp_base.params, self._base_dims) + mats(self.mlp_head.params, self._head_dims)
             if self.num_semantic_classes > 0:
-                blobs += mats(self.mlp_sem.params, self._sem_dims)
+                blobs += mats(self.mlp_sem.params, self._sem_dims_flat, rows=[a for a, _ in self._sem_dims])
             else:
                 blobs += [torch.zeros(a * b, dtype=torch.float16, device=dev) for a, b in self._sem_dims]
             weights = torch.cat(blobs).contiguous()
@@ -359,17 +389,19 @@ class NGPRadianceField(torch.nn.Module):
         with torch.no_grad():
             dev = self.mlp_base.params.device
 
-            def mats(flat, dims):
+            def mats(flat, dims, rows=None):
                 out, o = [], 0
-                for n_out, n_in in dims:
+                for i, (n_out, n_in) in enumerate(dims):
                     w = flat[o:o + n_out * n_in].reshape(n_out, n_in).to(torch.float16)
+                    if rows is not None and rows[i] > n_out:
+                        w = torch.cat([w, w.new_zeros((rows[i] - n_out, n_in))])
                     out.append(_umma_pack(w.t().contiguous()))
                     o += n_out * n_in
                 return out
 
             blobs = mats(self.mlp_base.params, self._base_dims) + mats(self.mlp_head.params, self._head_dims)
             if self.num_semantic_classes > 0:
-                blobs += mats(self.mlp_sem.params, self._sem_dims)
+                blobs += mats(self.mlp_sem.params, self._sem_dims_flat, rows=[a for a, _ in self._sem_dims])
             else:
                 blobs += [torch.zeros(a * b, dtype=torch.float16, device=dev) for a, b in self._sem_dims]
             self._cache_t = torch.cat(blobs).contiguous()

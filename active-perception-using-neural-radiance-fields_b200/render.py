@@ -141,6 +141,9 @@ class FusedRenderer:
         binaries = estimator.binaries.contiguous()
         aabbs = estimator.aabbs.contiguous().float()
         rx, ry, rz = (int(v) for v in binaries.shape[1:])
+        n_words = (rx * ry * rz + 31) // 32  # the marcher's one-bit-per-cell copy of the grid, rebuilt by render_init
+        if getattr(self, "occ_bits", None) is None or self.occ_bits.numel() < n_words:
+            self.occ_bits = torch.empty(n_words, device=self.device, dtype=torch.int32)
         weights, table = radiance_field._packed()
         aabb_host = radiance_field.aabb_host()
         meta = radiance_field._meta
@@ -152,7 +155,7 @@ class FusedRenderer:
         with torch.cuda.device(self.device):
             call("apnerf_render_init", n_rays, rays_per_call, rays_o, rays_d, rx, ry, rz, binaries, aabbs,
                  float(near_plane), self.n_state, state, self.t_min, self.t_max, self.hit, self.near, self.alive[1],
-                 self.n_alive_acc, self.iter_samples, self.total_samples, n_calls, self.counters)
+                 self.n_alive_acc, self.iter_samples, self.total_samples, n_calls, self.counters, self.occ_bits)
             # the per-iteration launch sequence, marshalled once (two variants: the live lists ping-pong)
             aabb_p = aabb_host.ctypes.data_as(ctypes.c_void_p)
             meta_p = meta.ctypes.data_as(ctypes.c_void_p)
@@ -167,7 +170,7 @@ class FusedRenderer:
                         "apnerf_render_march_tiles", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry,
                         rz, binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
                         float(render_step_size), float(cone_angle), self.s_ray, self.s_cnt, self.s_ts, self.s_te,
-                        aabb_p, self.s_x, self.keep_flag, int(s_cap), self.counters))
+                        aabb_p, self.s_x, self.keep_flag, int(s_cap), self.counters, self.occ_bits))
                     steps.append(PreparedCall(
                         "apnerf_field_forward_fused", self.counters[2:3], s_cap // 128, self.s_ray, self.s_cnt,
                         self.s_ts, self.s_te, self.s_x, rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights,
@@ -182,7 +185,7 @@ class FusedRenderer:
                         "apnerf_render_march", n_rays, rays_per_call, cur, self.n_samp, rays_o, rays_d, rx, ry, rz,
                         binaries, aabbs, self.t_min, self.t_max, self.hit, self.near, float(far_plane),
                         float(render_step_size), float(cone_angle), self.entry_base, self.entry_cnt, self.s_ray,
-                        self.s_ts, self.s_te, aabb_p, self.s_x, self.counters))
+                        self.s_ts, self.s_te, aabb_p, self.s_x, self.counters, self.occ_bits))
                     steps.append(PreparedCall(
                         "apnerf_field_forward_rows", self.counters[2:3], (s_cap + 127) // 128, self.s_ray, self.s_x,
                         rays_d, aabb_p, radiance_field.n_levels, meta_p, table, weights, self.rows))

@@ -132,6 +132,9 @@ class PredictiveInformationScorer:
                         st = self._states[slot][m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
                         states.append(st)
                         r = self.renderers[slot][m]
+                        if e.binaries.shape[0] != 1:  # multi-level grids: the op-by-op renderer, view by view
+                            self._render_unfused(f, e, rays_o, rays_d, st)
+                            continue
                         if not self.interleave:
                             r.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st, **self.opts)
                             if self.after_render is not None:
@@ -162,6 +165,25 @@ class PredictiveInformationScorer:
                     call("apnerf_score_views", E, states[0], states[1], states[2], states[3], nr, self.rays_per_view,
                          self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
         return sums
+
+    def _render_unfused(self, field, estimator, rays_o, rays_d, st):
+        """Fill the state planes the scorer reads (opacity, variances, semantic logits) from the op-by-op renderer,
+        one call per view as the reference does: the path for occupancy grids with more than one level."""
+        from .render import Rays, render_probablistic_image_with_occgrid_test_unfused
+
+        R = self.rays_per_view
+        for v0 in range(0, rays_o.shape[0], R):
+            rays = Rays(origins=rays_o[v0:v0 + R], viewdirs=rays_d[v0:v0 + R])
+            out = render_probablistic_image_with_occgrid_test_unfused(
+                self.opts["max_samples"], field, estimator, rays, near_plane=self.opts["near_plane"],
+                render_step_size=self.opts["render_step_size"], cone_angle=self.opts["cone_angle"],
+                alpha_thre=self.opts["alpha_thre"])
+            rgb_var, opacity, depth_var = out[1], out[2], out[4]
+            st[5:8, v0:v0 + R] = rgb_var.t()
+            st[8, v0:v0 + R] = depth_var[:, 0]
+            st[3, v0:v0 + R] = opacity[:, 0]
+            if self.n_sem > 0:
+                st[9:, v0:v0 + R] = out[5].t()
 
     # ---- multi-GPU view assignment ---------------------------------------------------------------------------
     @torch.no_grad()
@@ -205,7 +227,8 @@ class PredictiveInformationScorer:
 
         n = len(poses)
         lo, hi = shard_range(n, rank, world)
-        if world == 1 or self.balance == "contiguous" or n < 2 * world:
+        if (world == 1 or self.balance == "contiguous" or n < 2 * world
+                or any(e.binaries.shape[0] != 1 for e in self.estimators)):
             return np.arange(lo, hi)
         cap = (n + world - 1) // world
         est = torch.zeros(cap, device=self.device)
@@ -307,7 +330,8 @@ def probablistic_uncertainty(radiance_fields, estimators, trajectory, *, img_w, 
                              render_step_size, cone_angle, alpha_thre, scale=0.1, device="cuda:0", log=None) -> float:
     """Drop-in for the body of ActiveNeRFMapper.probablistic_uncertainty (pipeline.py:666-798):
     returns the trajectory's predictive information; appends the four logged terms to `log`."""
-    key = (id(radiance_fields[0]), img_w, img_h, float(focal), float(scale), str(device))
+    key = (tuple(id(f) for f in radiance_fields), tuple(id(e) for e in estimators), img_w, img_h, float(focal),
+           float(scale), str(device), float(near_plane), float(render_step_size), float(cone_angle), float(alpha_thre))
     scorer = _SCORERS.get(key)
     if scorer is None:
         scorer = PredictiveInformationScorer(radiance_fields, estimators, img_w, img_h, focal, near_plane=near_plane,

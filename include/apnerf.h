@@ -157,6 +157,15 @@ int apnerf_field_backward(long long n, const float* d_dens, const float* d_rgb, 
                           void* g_out_s, void* g_hh2, void* g_hs2, void* g_hh1, void* g_hs1, void* g_base,
                           void* g_h2, void* g_h1, float* d_enc, void* stream);
 
+/* Weight gradients of the three MLPs, dW = dY^T . X, as tcgen05 split-K products with all nine accumulators in TMEM
+ * (csrc/field_wgrad_kernel.cuh) -- the other half of tcnn's FullyFusedMLP backward behind loss.backward()
+ * (scripts/pipeline.py:518; ngp.py:123-169).  G [n_pad, 576] / X [n_pad, 624]: the fp16 matrices written by
+ * apnerf_field_backward (g_stride 576) and apnerf_field_forward_train (save_stride 624), rows >= n zero, n_pad a
+ * multiple of 32.  d_base / d_head / d_sem (fp32, += ; d_sem may be NULL): flat gradients of [W1|W2|W3],
+ * [WH1|WH2|WH3], [WS1|WS2|WS3] in tcnn's parameter order; sem_out_rows = rows of WS3 (16 or 32). */
+int apnerf_field_wgrad(long long n, const void* G, const void* X, float loss_scale, float* d_base, float* d_head,
+                       float* d_sem, int sem_out_rows, void* stream);
+
 /* OccGridEstimator._update -- perception/nerfacc/nerfacc/estimators/occ_grid.py:377-437, the per-level body
  * fused into the field kernel: x = level_aabb_lo + ((grid_coords(cell) + jitter) / res) * extent; occ =
  * query_density(x) * occ_scale (the pipeline's occ_eval_fn, scripts/pipeline.py:470-475); occs_new[cell] =
@@ -200,7 +209,7 @@ int apnerf_render_init(int n_rays, int rays_per_call, const float* rays_o, const
                        int ry, int rz, const uint8_t* binaries, const float* aabbs, float near_plane,
                        int n_state, float* state, float* t_min, float* t_max, uint8_t* hit, float* near,
                        int* alive, int* n_alive_acc, int* iter_samples, int* total_samples, int n_calls,
-                       int* counters, void* stream);
+                       int* counters, uint32_t* occ_bits, void* stream);
 /* utils.py:896-903: per call n = max(min(R // n_alive, 64), min_samples), iter_samples += n. */
 int apnerf_render_schedule(int n_calls, int rays_per_call, int max_samples, int min_samples,
                            int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, void* stream);
@@ -213,7 +222,8 @@ int apnerf_render_march(int max_live, int rays_per_call, const int* alive, const
                         const uint8_t* binaries, const float* aabbs, const float* t_min, const float* t_max,
                         const uint8_t* hit, float* near, float far_plane, float step_size, float cone_angle,
                         int* entry_base, int* entry_cnt, int* s_ray, float* s_ts, float* s_te,
-                        const float* field_aabb_host, void* s_x, int* counters, void* stream);
+                        const float* field_aabb_host, void* s_x, int* counters, const uint32_t* occ_bits,
+                        void* stream);
 /* utils.py:937-1009: weights with prefix transmittance, alpha_thre filter, accumulation, variance
  * terms, next ray mask, live-list compaction.  rows: the field kernel's packed fp16 rows
  * [s][40]; density = exp(logit - 1) (ngp.py:79), rgb = sigmoid(logit) (ngp.py:211-212).
@@ -253,7 +263,7 @@ int apnerf_render_march_tiles(int max_live, int rays_per_call, const int* alive,
                               const float* t_max, const uint8_t* hit, float* near, float far_plane,
                               float step_size, float cone_angle, int* s_ray, uint8_t* s_cnt, float* s_ts,
                               float* s_te, const float* field_aabb_host, void* s_x, uint8_t* keep_flag, int s_cap,
-                              int* counters, void* stream);
+                              int* counters, const uint32_t* occ_bits, void* stream);
 int apnerf_field_forward_fused(const int* n_rows_dev, long long max_tiles, const int* s_ray,
                                const uint8_t* s_cnt, const float* s_ts, const float* s_te, const void* s_x,
                                const float* rays_d, const float* aabb_host,

@@ -263,3 +263,41 @@ def test_training_without_semantics_and_edge_inputs(apnerf):
     e = f(pos[:0], dirs[:0])
     assert e[0].shape == (0, 3) and e[1].shape == (0, 1)
     (e[0].sum() + e[1].sum()).backward()
+
+
+@pytest.mark.parametrize("n,C", [(1, 29), (31, 29), (4096 + 17, 29), (70001, 5), (150000, 0)])
+def test_wgrad_tcgen05_matches_library_gemm(apnerf, n, C):
+    """apnerf_field_wgrad (tcgen05 split-K, MN-major operands, nine accumulators in TMEM) against the same nine
+    products done by a library GEMM on the same fp16 matrices.  fp16 x fp16 products are exact in fp32, so the two
+    differ only by the fp32 summation order (up to 1.5e5 terms): 2e-4 of each block's largest entry."""
+    from apnerf._lib import call
+    from apnerf.radiance_fields import ngp
+
+    g = torch.Generator().manual_seed(n)
+    n_pad = ngp._padded_rows(n)
+    X = torch.zeros((n_pad, ngp._X_WIDTH), dtype=torch.float16)
+    G = torch.zeros((n_pad, ngp._G_WIDTH), dtype=torch.float16)
+    X[:n] = torch.randn((n, ngp._X_WIDTH), generator=g).clamp_min(0).half()       # ReLU-like activations
+    G[:n] = (torch.randn((n, ngp._G_WIDTH), generator=g) * 0.05).half()
+    X, G = X.to(DEV), G.to(DEV)
+    field = apnerf.NGPRadianceField([0, 0, 0, 1, 1, 1], layers=2, num_semantic_classes=C).to(DEV)
+    n_sem_flat = sum(a * b for a, b in field._sem_dims_flat)
+    out = [torch.zeros(field._n_base_w, device=DEV), torch.zeros(7168, device=DEV),
+           torch.zeros(n_sem_flat, device=DEV) if C > 0 else None]
+    ref = [torch.zeros_like(o) if o is not None else None for o in out]
+    call("apnerf_field_wgrad", n, G, X, float(ngp.LOSS_SCALE), out[0], out[1], out[2],
+         field._sem_dims_flat[2][0] if C > 0 else 32)
+    ngp._wgrad_library(field, G, X, ref[0], ref[1], ref[2])
+    torch.cuda.synchronize()
+    dims = [field._base_dims, field._head_dims, field._sem_dims_flat if C > 0 else []]
+    for o, r, dd in zip(out, ref, dims):
+        if o is None:
+            continue
+        off = 0
+        for a, b in dd:
+            blk_o, blk_r = o[off:off + a * b], r[off:off + a * b]
+            scale = float(blk_r.abs().max())
+            assert scale > 0
+            err = float((blk_o - blk_r).abs().max())
+            assert err <= 2e-4 * scale + 1e-7, (n, C, (a, b), err, scale)
+            off += a * b
