@@ -338,7 +338,7 @@ APNERF_API int apnerf_field_forward_rows(const int* n_rows_dev, long long max_ti
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward_rows: bad level table");
   FieldConst fc;
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
-  const int sms = apnerf_num_sms();
+  const int sms = apnerf_field_sms();
   const int grid = (int)(max_tiles < 1 ? 1 : (max_tiles < sms ? max_tiles : sms));
   return launch_field<3>(io, m, fc, grid, FIELD_SMEM_MIN, (cudaStream_t)stream, "field_forward_kernel(rows)");
 }

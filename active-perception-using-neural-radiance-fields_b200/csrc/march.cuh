@@ -21,9 +21,10 @@ struct GridView {
                          // 8x less cache footprint than the bool bytes, which is what the serial per-cell walk waits on
 };
 
-__device__ __forceinline__ bool cell_occupied(const GridView& g, const uint8_t* __restrict__ lvl_bin,
-                                              const uint32_t* __restrict__ lvl_bits, int cid) {
-  if (lvl_bits) return (__ldg(lvl_bits + (cid >> 5)) >> (cid & 31)) & 1u;
+template <bool BITS>
+__device__ __forceinline__ bool cell_occupied(const uint8_t* __restrict__ lvl_bin, const uint32_t* __restrict__ lvl_bits,
+                                              int cid) {
+  if (BITS) return (__ldg(lvl_bits + (cid >> 5)) >> (cid & 31)) & 1u;
   return lvl_bin[cid] != 0;
 }
 
@@ -113,7 +114,8 @@ __device__ __forceinline__ float skip_to(float t, float dt, float target, float 
 // (#samples + #runs) and `t_term` the terminate plane (grid.cu:274-280).
 // FAST (the renderer's instantiation): step_size > 0 is known and the closed-form skip is compiled out (an empty
 // 0.1 m cell is at most ~100 steps; the closed form only pays for pathological skips, see skip_to), which removes
-// eight instructions of uniform tests from every cell visit.
+// eight instructions of uniform tests from every cell visit; it also reads the occupancy from the bit-packed copy
+// (g.bits must be set).
 template <bool FAST = false, class Sink>
 __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], const float d[3],
                                          float near_plane, float far_plane,
@@ -189,11 +191,11 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
     }
     const int n_cells = g.rx * g.ry * g.rz;
     const uint8_t* __restrict__ lvl_bin = g.binaries + (int64_t)level * n_cells;
-    const uint32_t* __restrict__ lvl_bits = g.bits ? g.bits + (int64_t)level * ((n_cells + 31) >> 5) : nullptr;
+    const uint32_t* __restrict__ lvl_bits = FAST ? g.bits + (int64_t)level * ((n_cells + 31) >> 5) : nullptr;
 
     // The walk over the cells is a serial chain whose longest link is the occupancy load, so the NEXT cell's occupancy
     // is fetched before the current cell is processed: which cell comes next depends only on tdist, not on the samples.
-    bool occ = cell_occupied(g, lvl_bin, lvl_bits, cid);
+    bool occ = cell_occupied<FAST>(lvl_bin, lvl_bits, cid);
     while (limit <= 0 || n_samples < limit) {  // grid.cu:184
       const float t_traverse = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
       // single_traversal, include/utils_grid.cuh:116-142: step along the axis with the nearest boundary
@@ -202,7 +204,7 @@ __device__ __forceinline__ int march_ray(const GridView& g, const float o[3], co
       const int next_cid = cid + (m0 ? idstep[0] : (m1 ? idstep[1] : idstep[2]));
       const int left = (m0 ? cnt[0] : (m1 ? cnt[1] : cnt[2])) - 1;
       bool occ_next = false;
-      if (left != 0 && (unsigned)next_cid < (unsigned)n_cells) occ_next = cell_occupied(g, lvl_bin, lvl_bits, next_cid);
+      if (left != 0 && (unsigned)next_cid < (unsigned)n_cells) occ_next = cell_occupied<FAST>(lvl_bin, lvl_bits, next_cid);
       if (!occ) {
         if (free_step) {
           t_last = t_traverse;

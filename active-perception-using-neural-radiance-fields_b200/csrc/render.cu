@@ -162,7 +162,7 @@ struct LocalSink {
 // append them to the compact per-iteration sample list (warp-aggregated reservation keeps the
 // samples of neighbouring rays adjacent, which is what gives the hash-grid gather its locality).
 template <bool FAST>
-__global__ void __launch_bounds__(256, 5) render_march_kernel(const int* counters_in, int rays_per_call,
+__global__ void __launch_bounds__(256, 4) render_march_kernel(const int* counters_in, int rays_per_call,
                                                            const int* __restrict__ alive, const int* __restrict__ n_samp,
                                                            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                            GridView g, const float* __restrict__ t_min,
@@ -784,7 +784,7 @@ APNERF_API int apnerf_render_march(int max_live, int rays_per_call, const int* a
   for (int i = 0; i < 6; ++i) fc.aabb[i] = field_aabb_host[i];
   int mt, mc;
   apnerf_march_cfg(mt, mc);
-  auto kernel = step_size > 0.0f ? render_march_kernel<true> : render_march_kernel<false>;
+  auto kernel = (step_size > 0.0f && occ_bits) ? render_march_kernel<true> : render_march_kernel<false>;
   kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, entry_base, entry_cnt, s_ray, s_ts, s_te, fc, (float4*)s_x, counters);
@@ -806,7 +806,7 @@ APNERF_API int apnerf_render_march_tiles(int max_live, int rays_per_call, const 
   for (int i = 0; i < 6; ++i) fc.aabb[i] = field_aabb_host[i];
   int mt, mc;
   apnerf_march_cfg(mt, mc);
-  auto kernel = step_size > 0.0f ? render_march_tiles_kernel<true> : render_march_tiles_kernel<false>;
+  auto kernel = (step_size > 0.0f && occ_bits) ? render_march_tiles_kernel<true> : render_march_tiles_kernel<false>;
   kernel<<<grid_for(max_live, mt, mc), mt, 0, (cudaStream_t)stream>>>(
       counters, rays_per_call, alive, n_samp, rays_o, rays_d, g, t_min, t_max, hit, near, far_plane, step_size,
       cone_angle, s_ray, s_cnt, s_ts, s_te, fc, (float4*)s_x, keep_flag, s_cap, counters);

@@ -9,6 +9,8 @@ reduces them in float64 numpy) and the planner's loop over trajectories (pipelin
 folded into one batch.  Multi-GPU: views are sharded over ranks, each rank reduces its views to
 per-trajectory partial sums, and ONE all-reduce of [n_traj, 4] float64 finishes the job.
 """
+import collections
+import os
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -84,6 +86,7 @@ class PredictiveInformationScorer:
         self.renderer = self.renderers[0][0]
         self._streams = None
         self.interleave = True  # False: one render after the other on the current stream (measurement)
+        self.stagger_iters = int(os.environ.get("APNERF_STAGGER", "12"))  # a batch leaves its head phase after this many marching iterations (see partial_sums)
         self._states = None
         self._rays = None
 
@@ -116,54 +119,72 @@ class PredictiveInformationScorer:
             if self._streams is None:
                 self._streams = [[torch.cuda.Stream(device=self.device) for _ in range(E)] for _ in range(K)]
             main = torch.cuda.current_stream()
-            batches = [(v0, min(n_views, v0 + vb)) for v0 in range(0, n_views, vb)]
-            for g0 in range(0, len(batches), K):
-                group = batches[g0:g0 + K]
-                gens, work = [], []
-                for slot, (v0, v1) in enumerate(group):
-                    nr = (v1 - v0) * self.rays_per_view
-                    rays_o, rays_d = self._rays[slot][0][:nr], self._rays[slot][1][:nr]
-                    call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
-                         self.rays_per_view, self.keep_idx, rays_o, rays_d)
-                    ready = torch.cuda.Event()
-                    ready.record(main)
-                    states = []
-                    for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
-                        st = self._states[slot][m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
-                        states.append(st)
-                        r = self.renderers[slot][m]
-                        if e.binaries.shape[0] != 1:  # multi-level grids: the op-by-op renderer, view by view
-                            self._render_unfused(f, e, rays_o, rays_d, st)
-                            continue
-                        if not self.interleave:
-                            r.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st, **self.opts)
-                            if self.after_render is not None:
-                                self.after_render(r)
-                            continue
+            batches = collections.deque((v0, min(n_views, v0 + vb)) for v0 in range(0, n_views, vb))
+            free_slots = list(range(K))
+            active = []  # batches in flight: dict(slot, v0, v1, nr, states, gens = [[stream, generator, iterations]])
+
+            def start(v0, v1, slot):
+                nr = (v1 - v0) * self.rays_per_view
+                rays_o, rays_d = self._rays[slot][0][:nr], self._rays[slot][1][:nr]
+                call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
+                     self.rays_per_view, self.keep_idx, rays_o, rays_d)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                states, gens = [], []
+                for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
+                    st = self._states[slot][m].view(-1)[: (9 + self.n_sem) * nr].view(9 + self.n_sem, nr)
+                    states.append(st)
+                    r = self.renderers[slot][m]
+                    if e.binaries.shape[0] != 1:  # multi-level grids: the op-by-op renderer, view by view
+                        self._render_unfused(f, e, rays_o, rays_d, st)
+                    elif not self.interleave:
+                        r.render(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st, **self.opts)
+                        if self.after_render is not None:
+                            self.after_render(r)
+                    else:
                         self._streams[slot][m].wait_event(ready)
-                        gens.append((self._streams[slot][m],
-                                     r.render_iter(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True,
-                                                   state=st, **self.opts)))
-                    work.append((v0, v1, nr, states))
-                live = list(range(len(gens)))
-                while live:  # enqueue the renders' marching iterations round-robin, each on its own stream
-                    for i in list(live):
-                        with torch.cuda.stream(gens[i][0]):
-                            if next(gens[i][1], None) is None:
-                                live.remove(i)
-                for stream, _ in gens:
+                        gens.append([self._streams[slot][m],
+                                     r.render_iter(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
+                                                   **self.opts), 0])
+                return dict(slot=slot, v0=v0, v1=v1, nr=nr, states=states, gens=gens)
+
+            def finish(job):
+                for stream, _, _ in job["gens"]:
                     done = torch.cuda.Event()
                     done.record(stream)
                     main.wait_event(done)
                 if self.after_render is not None and self.interleave:
-                    for slot in range(len(group)):
-                        for r in self.renderers[slot]:
-                            with torch.cuda.stream(main):
-                                self.after_render(r)
-                for v0, v1, nr, states in work:
-                    states = states + [None] * (4 - len(states))
-                    call("apnerf_score_views", E, states[0], states[1], states[2], states[3], nr, self.rays_per_view,
-                         self.n_sem, view_traj[v0:v1].contiguous(), n_traj, sums)
+                    for r in self.renderers[job["slot"]]:
+                        self.after_render(r)
+                states = job["states"] + [None] * (4 - len(job["states"]))
+                call("apnerf_score_views", E, states[0], states[1], states[2], states[3], job["nr"], self.rays_per_view,
+                     self.n_sem, view_traj[job["v0"]:job["v1"]].contiguous(), n_traj, sums)
+                free_slots.append(job["slot"])
+
+            # Rolling pipeline.  The first dozen marching iterations of a batch are wide, throughput-bound launches; the
+            # long tail (a few views whose rays cross much transparent occupied space keep marching 4 samples at a time,
+            # up to 256 iterations) is a train of small latency-bound launches that leave most of the GPU idle.  A new
+            # batch is therefore started, on its own streams, as soon as every batch in flight has left its head phase:
+            # the next head's big kernels fill the SMs the tails do not use.
+            while batches or active:
+                head_done = all(g[2] >= self.stagger_iters or g[1] is None for job in active for g in job["gens"])
+                if batches and free_slots and (not active or head_done):
+                    v0, v1 = batches.popleft()
+                    active.append(start(v0, v1, free_slots.pop(0)))
+                for job in list(active):
+                    running = False
+                    for g in job["gens"]:  # one marching iteration per render, each on its own stream
+                        if g[1] is None:
+                            continue
+                        with torch.cuda.stream(g[0]):
+                            if next(g[1], None) is None:
+                                g[1] = None
+                            else:
+                                g[2] += 1
+                                running = True
+                    if not running:
+                        active.remove(job)
+                        finish(job)
         return sums
 
     def _render_unfused(self, field, estimator, rays_o, rays_d, st):

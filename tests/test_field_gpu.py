@@ -66,11 +66,17 @@ def test_field_forward_matches_oracle(apnerf, oracle, n):
     assert (density[outside] == 0).all()
     # density = exp(fp16 logit - 1): one fp16 ulp of the logit (2^-10 relative at |x|~1..2, more for
     # larger logits) is the expected deviation; allow 2 % relative
+    # Bounds on EVERY sample (no quantiles).  The two implementations accumulate the same fp16 products in fp32 in a
+    # different order, so an activation can round to the neighbouring fp16 value and the difference propagates:
+    # colour (after the sigmoid) stays within the north star's 1e-3; the density is exp(fp16 logit - 1), so one fp16
+    # ulp of a logit of magnitude 8..16 (2^-7) is ~1 % relative: 2 % bound; semantic logits 4e-3 of their range; and
+    # the samples beyond HALF of each bound are counted (<= 1 %).
     rel = np.abs(density - odens) / np.maximum(np.abs(odens), 1e-6)
-    assert np.quantile(rel, 0.999) <= 2e-2 and np.median(rel) <= 1e-3, (np.quantile(rel, 0.999), np.median(rel))
-    assert np.abs(rgb - orgb).max() <= 1e-3 * 4, np.abs(rgb - orgb).max()       # worst case
-    assert np.quantile(np.abs(rgb - orgb), 0.999) <= 1e-3                       # north_star tolerance
-    assert np.quantile(np.abs(sem - osem), 0.999) <= 4e-3 * max(1.0, np.abs(osem).max())
+    e_rgb, e_sem = np.abs(rgb - orgb), np.abs(sem - osem) / max(1.0, np.abs(osem).max())
+    print(f"field n={n}: max rel density {rel.max():.2e}, max |rgb| {e_rgb.max():.2e}, max |sem|/range {e_sem.max():.2e}; "
+          f"beyond half bound: {(rel > 1e-2).mean():.2e} {(e_rgb > 5e-4).mean():.2e} {(e_sem > 2e-3).mean():.2e}")
+    assert rel.max() <= 2e-2 and e_rgb.max() <= 1e-3 and e_sem.max() <= 4e-3, (rel.max(), e_rgb.max(), e_sem.max())
+    assert (rel > 1e-2).mean() <= 1e-2 and (e_rgb > 5e-4).mean() <= 1e-2 and (e_sem > 2e-3).mean() <= 1e-2
 
 
 def test_field_without_semantics(apnerf, oracle):
@@ -85,4 +91,4 @@ def test_field_without_semantics(apnerf, oracle):
         out = f(pos.to(DEV), dirs.to(DEV))
     assert len(out) == 2
     orgb, odens = oracle.field_forward(pos.numpy(), dirs.numpy(), np.asarray(AABB, np.float32), fp)
-    assert np.quantile(np.abs(out[0].cpu().numpy() - orgb), 0.999) <= 1e-3
+    assert np.abs(out[0].cpu().numpy() - orgb).max() <= 1e-3  # every sample, north-star colour tolerance

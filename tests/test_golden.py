@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch
 
+from bounds import assert_bounded, scale_of
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_python_path.npz")
 NAMES = ("rgb", "rgb_var", "opacity", "depth", "depth_var", "sem")
 
@@ -134,9 +136,8 @@ def test_oracle_trajectory_views_match_reference_python(apnerf, oracle, gold):
 @pytest.mark.parametrize("tag", ["a", "b"])
 def test_cuda_renderer_matches_reference_python(apnerf, gold, tag):
     """render_probablistic_image_with_occgrid_test (drop-in signature) on the golden rays.  Tolerances are the
-    north star's: fp16 MLP 1e-3 absolute on the network outputs -> 2e-3 (99 % quantile; a ray whose opacity
-    sits on the early-stop / alpha threshold may differ by one sample) and 1e-4 median, relative to the
-    output's largest value."""
+    north star's: every pixel of every output within 1e-3 of the output's range (fp16 MLP tolerance), except an
+    explicitly counted handful of threshold-flip pixels (tests/bounds.py)."""
     g, cfg = gold
     dev = "cuda:0"
     (field, est), _ = _members(apnerf, cfg, dev)
@@ -148,13 +149,14 @@ def test_cuda_renderer_matches_reference_python(apnerf, gold, tag):
         cone_angle=o["cone_angle"], alpha_thre=o["alpha_thre"])
     ref_total = int(g[f"view_{tag}_total_samples"])
     assert abs(int(got[6]) - ref_total) <= 0.02 * ref_total
+    pairs = []
     for name, a in zip(NAMES, got[:6]):
         ref = g[f"view_{tag}_{name}"]
         a = a.cpu().numpy()
         assert a.shape == ref.shape, name
-        scale = max(1.0, np.abs(ref).max())
-        assert np.median(np.abs(a - ref)) <= 1e-4 * scale, (name, np.median(np.abs(a - ref)))
-        assert np.quantile(np.abs(a - ref), 0.99) <= 2e-3 * scale, (name, np.quantile(np.abs(a - ref), 0.99))
+        pairs.append((name, a, ref, 1e-3 * scale_of(ref)))
+    # every pixel of every output within 1e-3 of the output's range, except a counted handful of threshold-flip pixels
+    assert_bounded(pairs, ref.shape[0] if ref.ndim == 2 else int(np.prod(ref.shape[:-1])), f"view {tag}")
 
 
 @pytest.mark.gpu
@@ -234,8 +236,8 @@ def test_cuda_sampling_and_rendering_match_reference_python(apnerf, gold):
 def test_cuda_render_wrappers_match_reference_python(apnerf, gold):
     """render_image_with_occgrid_with_depth_guide / render_image_with_occgrid / render_image_with_occgrid_test
     (utils.py:63-780) in eval mode.  The field is fp16 (1e-3 absolute on its outputs), and its density also
-    drives the visibility filter, so a few samples on the alpha threshold differ: 2 % on the sample count,
-    1e-4 median / 3e-3 at the 99 % quantile on the images."""
+    drives the visibility filter, so a few samples on the alpha threshold differ: 2 % on the sample count; every
+    pixel within 1e-3 of the output's range except a counted handful of threshold-flip pixels (tests/bounds.py)."""
     from apnerf import synthetic
 
     _, cfg = gold
@@ -256,13 +258,13 @@ def test_cuda_render_wrappers_match_reference_python(apnerf, gold):
     def check(prefix, got, names):
         n_ref = int(g[f"{prefix}_n"])
         assert abs(int(got[-1]) - n_ref) <= 0.02 * n_ref, (prefix, int(got[-1]), n_ref)
+        pairs = []
         for name, a in zip(names, got):
             ref = g[f"{prefix}_{name}"]
             a = a.cpu().numpy()
             assert a.shape == ref.shape, (prefix, name)
-            scale = max(1.0, np.abs(ref).max())
-            assert np.median(np.abs(a - ref)) <= 1e-4 * scale, (prefix, name, np.median(np.abs(a - ref)))
-            assert np.quantile(np.abs(a - ref), 0.99) <= 3e-3 * scale, (prefix, name, np.quantile(np.abs(a - ref), 0.99))
+            pairs.append((name, a, ref, 1e-3 * scale_of(ref)))
+        assert_bounded(pairs, w * h, prefix)
 
     with torch.no_grad():
         check("guide", apnerf.render_image_with_occgrid_with_depth_guide(
@@ -305,13 +307,13 @@ def test_cuda_training_mode_render_matches_reference_python(apnerf, gold, monkey
     assert got[0].requires_grad and got[3].requires_grad  # the differentiable path was taken
     n_ref = int(g["train_n"])
     assert abs(int(got[4]) - n_ref) <= 0.02 * n_ref, (int(got[4]), n_ref)
+    pairs = []
     for name, a in zip(("rgb", "opacity", "depth", "sem"), got[:4]):
         ref = g[f"train_{name}"]
         a = a.detach().cpu().numpy()
         assert a.shape == ref.shape, name
-        scale = max(1.0, np.abs(ref).max())
-        assert np.median(np.abs(a - ref)) <= 1e-4 * scale, (name, np.median(np.abs(a - ref)))
-        assert np.quantile(np.abs(a - ref), 0.99) <= 3e-3 * scale, (name, np.quantile(np.abs(a - ref), 0.99))
+        pairs.append((name, a, ref, 1e-3 * scale_of(ref)))
+    assert_bounded(pairs, w * h, "train-mode render")
 
 
 @pytest.mark.gpu
@@ -356,9 +358,8 @@ def test_cuda_dataset_entry_points_match_reference_python(apnerf, gold):
 
     def close(a, ref, what):
         assert a.shape == ref.shape and a.dtype == np.float64, (what, a.shape, ref.shape, a.dtype)
-        scale = max(1.0, np.abs(ref).max())
-        assert np.median(np.abs(a - ref)) <= 1e-4 * scale, (what, np.median(np.abs(a - ref)))
-        assert np.quantile(np.abs(a - ref), 0.99) <= 3e-3 * scale, (what, np.quantile(np.abs(a - ref), 0.99))
+        n_pix = int(np.prod(ref.shape[:3]))  # [K, h, w(, D)]
+        assert_bounded([(str(what), a, ref, 1e-3 * scale_of(ref))], n_pix, str(what))
 
     traj = g["traj_poses"]
     unc = apnerf.scoring.uncertainty_view_indices(len(traj))

@@ -128,15 +128,19 @@ def test_fused_render_matches_unfused_and_oracle(apnerf, oracle):
     opac = orc[2]
     assert 0.05 < (opac > 0.5).mean() < 1.0, "scene should have both saturated and open rays"
     assert abs(fused[6] - orc[6]) <= 0.02 * orc[6] and abs(unfused[6] - orc[6]) <= 0.02 * orc[6]
+    from bounds import assert_bounded, scale_of
+
+    vs_unfused, vs_oracle = [], []
     for name, a, b, c in zip(names, fused[:6], unfused[:6], orc[:6]):
         a, b = a.cpu().numpy(), b.cpu().numpy()
-        scale = max(1.0, np.abs(c).max())
-        # fused vs op-by-op on the same GPU: same field kernel, only the fp32 accumulation order differs
-        assert np.quantile(np.abs(a - b), 0.99) <= 1e-5 * scale, (name, np.quantile(np.abs(a - b), 0.99))
-        # vs the CPU oracle: fp16 MLP tolerance 1e-3 absolute on colour / entropy inputs (north star);
-        # a ray whose opacity sits on the early-stop threshold may stop one iteration apart -> quantile
-        assert np.median(np.abs(a - c)) <= 1e-4 * scale, (name, np.median(np.abs(a - c)))
-        assert np.quantile(np.abs(a - c), 0.99) <= 2e-3 * scale, (name, np.quantile(np.abs(a - c), 0.99))
+        vs_unfused.append((name, a, b, 1e-5 * scale_of(c)))
+        vs_oracle.append((name, a, c, 1e-3 * scale_of(c)))
+    # fused vs op-by-op on the same GPU: the field kernel's two entry points (sample rows / explicit points) evaluate the
+    # same network; the fp32 accumulation order of the compositing differs: 1e-5 of the range on every pixel but a
+    # counted handful whose samples sit on a threshold
+    assert_bounded(vs_unfused, w * h, "fused vs op-by-op")
+    # vs the CPU oracle: fp16 MLP tolerance 1e-3 of the range (north star) on every pixel except counted flip pixels
+    assert_bounded(vs_oracle, w * h, "fused vs oracle")
 
 
 def test_plain_renderer_and_no_semantics(apnerf):

@@ -66,8 +66,8 @@ def test_training_forward_matches_inference_kernel(apnerf):
     assert rgb1.requires_grad and dens1.requires_grad and sem1.requires_grad
     # same operands and rounding points; only the fp32 accumulation order inside the GEMMs differs
     assert (rgb0 - rgb1).abs().max() <= 1e-3
-    assert ((dens0 - dens1).abs() / dens0.clamp_min(1e-6)).quantile(0.999) <= 2e-2
-    assert (sem0 - sem1).abs().quantile(0.999) <= 4e-3
+    assert float(((dens0 - dens1).abs() / dens0.clamp_min(1e-6)).max()) <= 2e-2  # every sample: <= one fp16 ulp of the logit
+    assert float((sem0 - sem1).abs().max()) <= 4e-3 * max(1.0, float(sem0.abs().max()))
 
 
 def test_field_gradients_match_fp32_reference(apnerf):
@@ -131,7 +131,8 @@ def test_field_gradients_match_fp32_reference(apnerf):
         a, b = got[name], ref
         cos = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)
         rel = (a - b).norm() / b.norm()
-        assert cos > 0.995 and rel < 0.1, (name, float(cos), float(rel))
+        # fp16 activations and gradients (x128 loss scale) against an fp32 graph: measured 0.2-1 % (tools/train_grad_check.py)
+        assert cos > 0.9995 and rel < 2e-2, (name, float(cos), float(rel))
     assert got["direction_encoding.params"].numel() == 0 if "direction_encoding.params" in got else True
 
 
