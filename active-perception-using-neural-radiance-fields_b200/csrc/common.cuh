@@ -72,17 +72,6 @@ static inline float apnerf_skip_min_steps() {
   }
   return v;
 }
-// SMs the renderer's field kernel may occupy (it is persistent, one 832-thread CTA per SM, and nothing else fits
-// beside it): leaving a few SMs free lets the OTHER streams' march / composite launches run concurrently with it.
-static inline int apnerf_field_sms() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("APNERF_FIELD_SMS");
-    v = e ? atoi(e) : 0;
-  }
-  const int sms = apnerf_num_sms();
-  return (v > 0 && v < sms) ? v : sms;
-}
 static inline void apnerf_march_cfg(int& threads, int& ctas_per_sm) {
   static int t = 0, c = 0;
   if (t == 0) {

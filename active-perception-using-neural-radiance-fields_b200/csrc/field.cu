@@ -338,9 +338,16 @@ APNERF_API int apnerf_field_forward_rows(const int* n_rows_dev, long long max_ti
   APNERF_REQUIRE(fill_meta(m, n_levels, meta_host) == 0, "field_forward_rows: bad level table");
   FieldConst fc;
   for (int i = 0; i < 6; ++i) fc.aabb[i] = aabb_host[i];
-  const int sms = apnerf_field_sms();
+  const int sms = apnerf_num_sms();
   const int grid = (int)(max_tiles < 1 ? 1 : (max_tiles < sms ? max_tiles : sms));
-  return launch_field<3>(io, m, fc, grid, FIELD_SMEM_MIN, (cudaStream_t)stream, "field_forward_kernel(rows)");
+  // Coarse-level staging (north star (2)): measured on B200, staging level 0 in shared memory is SLOWER than leaving
+  // it to L1 (profiles/r02_field_kernel.md) -- L1 and shared memory are the same SRAM behind the same pipe, a level-0
+  // gather of 32 neighbouring samples is already a broadcast of one or two lines, and the 32 KB come out of the L1
+  // that caches the fine levels.  Kept as an experiment switch.
+  static const bool stage = getenv("APNERF_FIELD_STAGE_L0") && atoi(getenv("APNERF_FIELD_STAGE_L0")) != 0;
+  io.stage_level0 = stage ? 1 : 0;
+  return launch_field<3>(io, m, fc, grid, FIELD_SMEM_MIN + (stage ? FIELD_L0_BYTES : 0), (cudaStream_t)stream,
+                         "field_forward_kernel(rows)");
 }
 
 // The same with the compositor fused into the epilogue: sample rows (s_ray, s_cnt, s_ts, s_te, s_x; *n_rows_dev

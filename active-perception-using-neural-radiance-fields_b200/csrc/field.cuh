@@ -108,8 +108,11 @@ __device__ __forceinline__ uint2 ldg_entry(const uint2* __restrict__ level_base,
   return __ldg(reinterpret_cast<const uint2*>(addr));
 }
 
+// `staged`: optional copy of THIS level's entries in shared memory (the coarse-level staging of the north star; see
+// field_forward_kernel) -- the same entries, so the same result.
 __device__ __forceinline__ void gather_level(const HashGridMeta& m, int l, const float x[3],
-                                             const uint2* __restrict__ table, uint2 (&v)[8], float (&w)[3]) {
+                                             const uint2* __restrict__ table, uint2 (&v)[8], float (&w)[3],
+                                             const uint2* staged = nullptr) {
   uint32_t cell[3];
   level_cell(m, l, x, cell, w);
   const uint2* __restrict__ tl = table + m.offset[l];
@@ -135,6 +138,11 @@ __device__ __forceinline__ void gather_level(const HashGridMeta& m, int l, const
     } else {
       i0 %= size, i1 %= size, i2 %= size, i3 %= size, i4 %= size, i5 %= size, i6 %= size, i7 %= size;
     }
+  }
+  if (staged) {
+    v[0] = staged[i0], v[1] = staged[i1], v[2] = staged[i2], v[3] = staged[i3];
+    v[4] = staged[i4], v[5] = staged[i5], v[6] = staged[i6], v[7] = staged[i7];
+    return;
   }
   v[0] = ldg_entry(tl, i0), v[1] = ldg_entry(tl, i1), v[2] = ldg_entry(tl, i2), v[3] = ldg_entry(tl, i3);
   v[4] = ldg_entry(tl, i4), v[5] = ldg_entry(tl, i5), v[6] = ldg_entry(tl, i6), v[7] = ldg_entry(tl, i7);

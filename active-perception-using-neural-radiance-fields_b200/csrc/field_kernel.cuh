@@ -41,6 +41,7 @@ constexpr int SM_ACT = SM_BAR + 128;                              // N_CHAINS x 
 constexpr int ACT_BYTES = TILE_M * HID * 2;
 constexpr int FIELD_SMEM_MIN = SM_ACT;                            // 112 KB: weights + encode ring + barriers
 constexpr int FIELD_SMEM = SM_ACT + N_CHAINS * ACT_BYTES;         // + the fused compositor's per-chain scratch
+constexpr int FIELD_L0_BYTES = 32768;                             // optional staging of hash-grid level 0 (16^3 entries x 8 B)
 // Fused compositing scratch, one region per chain:
 constexpr int ROWBUF_BYTES = 5 * TILE_M * 16;                     // 5 chunks x [128 x 16 B] raw fp16 rows
 constexpr int ACT_ROWBUF = 0;
@@ -110,6 +111,8 @@ struct FieldIO {
   int* total_samples;           // [n_calls] composited (alpha_thre-visible) samples
   int probabilistic;            // accumulate the variance terms
   int* ray_counts;              // optional [2][n_rays_total]: += samples evaluated / composited per ray (tests)
+  int stage_level0;             // 1: copy level 0 of the table (<= 32 KB) into shared memory behind the kernel's own
+                                // regions and gather it from there (launch with FIELD_SMEM_MIN + FIELD_L0_BYTES)
   // --- training forward (kernel instantiation TRAIN): density / rgb get the raw fp16 logits (no exp / sigmoid /
   // selector) and the activations the backward kernel needs are saved (fp16, row-major) ---
   long long save_stride;        // elements between consecutive rows of every save_* matrix (they may be column
@@ -366,6 +369,13 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
   // ---- one-time setup: weights -> smem, barriers, TMEM ----
   for (int i = threadIdx.x; i < W_BYTES / 16; i += FIELD_THREADS)
     reinterpret_cast<uint4*>(smem + SM_W)[i] = __ldg(io.weights + i);
+  // optional: level 0 of the hash grid (the one level every sample of a tile shares cells of) staged in shared memory
+  const uint2* staged_l0 = nullptr;
+  if (MODE == 3 && io.stage_level0 && meta.size[0] * 8u <= (uint32_t)FIELD_L0_BYTES) {
+    uint2* dst = reinterpret_cast<uint2*>(smem + SM_ACT);
+    for (uint32_t i = threadIdx.x; i < meta.size[0]; i += FIELD_THREADS) dst[i] = __ldg(io.table + meta.offset[0] + i);
+    staged_l0 = dst;
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < A0_STAGES; ++i) {
       ptx::mbar_init(bar_full + 8 * i, N_ENC_THREADS);
@@ -424,7 +434,7 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       const int lv[4] = {2 * part, 2 * part + 1, 2 * part + 8, 2 * part + 9};
       uint2 f[4], va[8], vb[8];
       float wa[3], wb[3];
-      gather_level(meta, min(lv[0], nl1), x, io.table, va, wa);
+      gather_level(meta, min(lv[0], nl1), x, io.table, va, wa, part == 0 ? staged_l0 : nullptr);
       gather_level(meta, min(lv[1], nl1), x, io.table, vb, wb);
       f[0] = blend_level(wa, va);
       gather_level(meta, min(lv[2], nl1), x, io.table, va, wa);

@@ -572,7 +572,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--views-per-gpu", type=int, default=256, help="poses per rank with --scaling weak")
     ap.add_argument("--views-per-batch", type=int, default=64, help="views rendered per renderer pass")
-    ap.add_argument("--concurrent-batches", type=int, default=1,
+    ap.add_argument("--concurrent-batches", type=int, default=3,
                     help="view batches rendered concurrently per GPU (each x the ensemble members, own streams)")
     ap.add_argument("--balance", default="lpt", choices=["lpt", "contiguous"],
                     help="multi-GPU view assignment: balanced by estimated samples, or contiguous slices")
