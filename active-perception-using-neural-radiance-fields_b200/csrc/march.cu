@@ -102,6 +102,51 @@ __global__ void __launch_bounds__(256) traverse_kernel(int n_rays, const float* 
   }
 }
 
+// OccGridEstimator.sampling's use of the traversal (occ_grid.py:117-131): only the samples' (ray, t_start, t_end)
+// triples are needed there, i.e. intervals.vals[is_left] / [is_right] of the reference -- written directly, without the
+// interval edges, masks and the two boolean compactions (each a host synchronisation) in between.
+struct PairSink {
+  int64_t* ray_indices;
+  float* t_starts;
+  float* t_ends;
+  int64_t base, tid;
+  bool write;
+  __device__ __forceinline__ void operator()(float t_last, float t_next, bool, int i_sample, int) {
+    if (!write) return;
+    ray_indices[base + i_sample] = tid;
+    t_starts[base + i_sample] = t_last;
+    t_ends[base + i_sample] = t_next;
+  }
+};
+
+__global__ void __launch_bounds__(256) sample_rays_kernel(int n_rays, const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, GridView g,
+                                                          const uint8_t* __restrict__ hits,
+                                                          const float* __restrict__ t_sorted,
+                                                          const int64_t* __restrict__ t_indices,
+                                                          const float* __restrict__ near_planes,
+                                                          const float* __restrict__ far_planes, float step_size,
+                                                          float cone_angle, int limit,
+                                                          const int64_t* __restrict__ chunk_starts,
+                                                          int64_t* __restrict__ chunk_cnts,
+                                                          int64_t* __restrict__ ray_indices,
+                                                          float* __restrict__ t_starts, float* __restrict__ t_ends) {
+  const bool fill = chunk_starts != nullptr;
+  for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n_rays; tid += blockDim.x * gridDim.x) {
+    if (fill && chunk_cnts[tid] == 0) continue;
+    PairSink sink{ray_indices, t_starts, t_ends, fill ? chunk_starts[tid] : 0, tid, fill};
+    const float o[3] = {rays_o[3 * tid], rays_o[3 * tid + 1], rays_o[3 * tid + 2]};
+    const float d[3] = {rays_d[3 * tid], rays_d[3 * tid + 1], rays_d[3 * tid + 2]};
+    int n_intervals;
+    float t_term;
+    const int n_samples =
+        march_ray(g, o, d, near_planes[tid], far_planes[tid], hits + (size_t)tid * g.n_grids,
+                  t_sorted + (size_t)tid * g.n_grids * 2, t_indices ? t_indices + (size_t)tid * g.n_grids * 2 : nullptr,
+                  step_size, cone_angle, limit, sink, n_intervals, t_term);
+    if (!fill) chunk_cnts[tid] = n_samples;
+  }
+}
+
 // ---- int64 exclusive scan (chunk_cnts -> chunk_starts + total), replaces the reference's
 // torch::cumsum in RaySegmentsSpec::memalloc_data_from_chunk (data_spec.hpp:86-96).
 constexpr int SCAN_T = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_T * SCAN_ITEMS;
@@ -216,6 +261,26 @@ APNERF_API int apnerf_traverse_grids(int n_rays, const float* rays_o, const floa
       n_rays, rays_o, rays_d, rays_mask, g, hits, t_sorted, t_indices, near_planes, far_planes, step_size,
       cone_angle, traverse_steps_limit, first_pass != 0, iv, sm, terminate_planes);
   APNERF_CHECK_LAUNCH("traverse_kernel");
+  return 0;
+}
+
+// Samples of every ray as packed (ray_indices, t_starts, t_ends): chunk_starts == NULL counts (chunk_cnts written),
+// otherwise fills at chunk_starts[ray].
+APNERF_API int apnerf_sample_rays(int n_rays, const float* rays_o, const float* rays_d, int n_grids, int rx, int ry,
+                                  int rz, const uint8_t* binaries, const float* aabbs, const uint8_t* hits,
+                                  const float* t_sorted, const int64_t* t_indices, const float* near_planes,
+                                  const float* far_planes, float step_size, float cone_angle, int traverse_steps_limit,
+                                  const int64_t* chunk_starts, int64_t* chunk_cnts, int64_t* ray_indices,
+                                  float* t_starts, float* t_ends, void* stream) {
+  if (n_rays == 0) return 0;
+  APNERF_REQUIRE(n_grids >= 1 && n_grids <= 8, "sample_rays: n_grids must be in [1, 8]");
+  APNERF_REQUIRE(chunk_cnts != nullptr, "sample_rays: chunk_cnts is required");
+  APNERF_REQUIRE(chunk_starts == nullptr || (ray_indices && t_starts && t_ends), "sample_rays: null output");
+  GridView g{binaries, aabbs, n_grids, rx, ry, rz, apnerf_skip_min_steps()};
+  sample_rays_kernel<<<grid_for(n_rays, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      n_rays, rays_o, rays_d, g, hits, t_sorted, t_indices, near_planes, far_planes, step_size, cone_angle,
+      traverse_steps_limit, chunk_starts, chunk_cnts, ray_indices, t_starts, t_ends);
+  APNERF_CHECK_LAUNCH("sample_rays_kernel");
   return 0;
 }
 

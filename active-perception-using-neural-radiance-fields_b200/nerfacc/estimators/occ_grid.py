@@ -10,7 +10,7 @@ from typing import Callable, List, Optional, Tuple, Union
 import torch
 from torch import Tensor
 
-from ..grid import _enlarge_aabb, traverse_grids
+from ..grid import _enlarge_aabb, sample_rays, traverse_grids  # noqa: F401
 from ..volrend import render_visibility_from_alpha, render_visibility_from_density
 
 
@@ -80,16 +80,12 @@ class OccGridEstimator(torch.nn.Module):
             far_planes = torch.clamp(far_planes, max=t_max)
         if stratified:
             near_planes += torch.rand_like(near_planes) * render_step_size
-        intervals, samples, _ = traverse_grids(
-            rays_o, rays_d, self.binaries, self.aabbs, near_planes=near_planes, far_planes=far_planes,
-            step_size=render_step_size, cone_angle=cone_angle)
-        t_starts = intervals.vals[intervals.is_left]
-        t_ends = intervals.vals[intervals.is_right]
-        ray_indices = samples.ray_indices
-        packed_info = samples.packed_info
+        # traverse_grids + the two boolean compactions of the reference (:117-131) as one count / scan / fill
+        ray_indices, t_starts, t_ends, packed_info = sample_rays(
+            rays_o, rays_d, self.binaries, self.aabbs, near_planes, far_planes, render_step_size, cone_angle)
 
         if (alpha_thre > 0.0 or early_stop_eps > 0.0) and (sigma_fn is not None or alpha_fn is not None):
-            alpha_thre = min(alpha_thre, self.occs.mean().item())
+            alpha_thre = min(alpha_thre, self._occs_mean())
             if sigma_fn is not None:
                 if t_starts.shape[0] != 0:
                     sigmas = sigma_fn(t_starts, t_ends, ray_indices)
@@ -107,8 +103,19 @@ class OccGridEstimator(torch.nn.Module):
                 assert alphas.shape == t_starts.shape, "alphas must have shape of (N,)! Got {}".format(alphas.shape)
                 masks = render_visibility_from_alpha(
                     alphas=alphas, packed_info=packed_info, early_stop_eps=early_stop_eps, alpha_thre=alpha_thre)
-            ray_indices, t_starts, t_ends = ray_indices[masks], t_starts[masks], t_ends[masks]
+            keep = masks.nonzero(as_tuple=True)[0]  # ONE host sync for the three compactions (the reference has three)
+            ray_indices, t_starts, t_ends = ray_indices[keep], t_starts[keep], t_ends[keep]
         return ray_indices, t_starts, t_ends
+
+    def _occs_mean(self) -> float:
+        """``self.occs.mean().item()`` (occ_grid.py:199) without a host synchronisation per call: the occupancy values
+        only change when the grid is updated (every 16 training steps), so the mean is read back once per version of
+        the buffer."""
+        key = (self.occs.data_ptr(), self.occs._version)
+        if getattr(self, "_occs_mean_key", None) != key:
+            self._occs_mean_val = self.occs.mean().item()
+            self._occs_mean_key = key
+        return self._occs_mean_val
 
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2,

@@ -125,6 +125,39 @@ def traverse_grids(
     return intervals, samples, terminate_planes
 
 
+@torch.no_grad()
+def sample_rays(rays_o: Tensor, rays_d: Tensor, binaries: Tensor, aabbs: Tensor, near_planes: Tensor, far_planes: Tensor,
+                step_size: float, cone_angle: float):
+    """What ``OccGridEstimator.sampling`` takes from ``traverse_grids`` (occ_grid.py:117-131) -- the packed samples
+    ``(ray_indices i64, t_starts, t_ends, packed_info [n_rays, 2] i64)`` -- through ``apnerf_sample_rays``: count,
+    scan, fill; ONE host synchronisation (the sample total) where the interval route has four."""
+    require_cuda(rays_o, rays_d, binaries, aabbs)
+    rays_o, rays_d = rays_o.float().contiguous(), rays_d.float().contiguous()
+    binaries, aabbs = binaries.bool().contiguous(), aabbs.float().contiguous()
+    near_planes, far_planes = near_planes.float().contiguous(), far_planes.float().contiguous()
+    n_rays, n_grids = rays_o.shape[0], binaries.shape[0]
+    rx, ry, rz = (int(s) for s in binaries.shape[1:])
+    dev = rays_o.device
+    t_mins, t_maxs, hits = ray_aabb_intersect(rays_o, rays_d, aabbs)
+    if n_grids > 1:
+        t_sorted, t_indices = torch.sort(torch.cat([t_mins, t_maxs], dim=-1), dim=-1)
+        t_sorted, t_indices = t_sorted.contiguous(), t_indices.contiguous()
+    else:
+        t_sorted, t_indices = torch.cat([t_mins, t_maxs], dim=-1).contiguous(), None
+    cnts = torch.empty(n_rays, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        args = (n_rays, rays_o, rays_d, n_grids, rx, ry, rz, binaries, aabbs, hits.contiguous(), t_sorted, t_indices,
+                near_planes, far_planes, float(step_size), float(cone_angle), -1)
+        call("apnerf_sample_rays", *args, None, cnts, None, None, None)
+        starts, total = _exclusive_scan_i64(cnts)
+        n = int(total.item())
+        ray_indices = torch.empty(n, device=dev, dtype=torch.int64)
+        t_starts, t_ends = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        if n:
+            call("apnerf_sample_rays", *args, starts, cnts, ray_indices, t_starts, t_ends)
+    return ray_indices, t_starts, t_ends, torch.stack([starts, cnts], -1)
+
+
 def _enlarge_aabb(aabb, factor: float) -> Tensor:
     center = (aabb[:3] + aabb[3:]) / 2
     extent = (aabb[3:] - aabb[:3]) / 2

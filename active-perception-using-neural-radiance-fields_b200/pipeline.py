@@ -52,7 +52,7 @@ class ActiveNeRFMapper:
                tuple(sorted(self._render_opts().items())), c["img_w"], c["img_h"])
         if self._scorer is None or self._scorer[0] != key:
             s = PredictiveInformationScorer(self.radiance_fields, self.estimators, c["img_w"], c["img_h"], self.focal,
-                                            scale=scale, device=self.device, views_per_batch=c.get("views_per_batch", 160),
+                                            scale=scale, device=self.device, views_per_batch=c.get("views_per_batch"),
                                             **self._render_opts())
             self._scorer = (key, s)
         return self._scorer[1]

@@ -52,11 +52,13 @@ def uncertainty_view_indices(traj_len: int) -> np.ndarray:
 
 class PredictiveInformationScorer:
     """Renders views x ensemble members with the fused renderer and scores them on the device."""
+    _instances = 0
 
     def __init__(self, radiance_fields: Sequence[torch.nn.Module], estimators: Sequence[torch.nn.Module], width: int,
                  height: int, focal: float, *, near_plane: float = 0.1, render_step_size: float = 1e-3,
                  cone_angle: float = 0.004, alpha_thre: float = 0.01, scale: float = 1.0, max_samples: int = 1024,
-                 device="cuda:0", views_per_batch: int = 32, concurrent_batches: int = 1, balance: str = "lpt"):
+                 device="cuda:0", views_per_batch: Optional[int] = None, concurrent_batches: int = 3,
+                 balance: str = "lpt"):
         assert 1 <= len(radiance_fields) <= 4 and len(radiance_fields) == len(estimators)
         self.fields, self.estimators = list(radiance_fields), list(estimators)
         self.width, self.height, self.focal = int(width), int(height), float(focal)
@@ -64,11 +66,13 @@ class PredictiveInformationScorer:
                          alpha_thre=alpha_thre, max_samples=max_samples)
         self.device = torch.device(device)
         self.n_sem = self.fields[0].num_semantic_classes
-        self.views_per_batch = int(views_per_batch)
-        assert balance in ("lpt", "contiguous")
+        assert balance in ("lpt", "dynamic", "contiguous")
         self.balance = balance
         self.after_render = None  # optional callable(renderer), invoked once per finished render (measurement)
         self._probe = None
+        self._calls = 0
+        PredictiveInformationScorer._instances += 1
+        self._uid = PredictiveInformationScorer._instances  # the same on every rank (scorers are created in lock step)
         # rounded-linspace subsample of the full image (habitat_to_data.py:462-467)
         h, w = int(height * scale), int(width * scale)
         self.rays_per_view = h * w
@@ -77,6 +81,8 @@ class PredictiveInformationScorer:
         else:
             idx = np.round(np.linspace(0, width * height - 1, self.rays_per_view)).astype(np.int32)
             self.keep_idx = torch.from_numpy(idx).to(self.device)
+        # views per renderer pass: about 5 M rays (64 views of 320x240; 1200 views of 64x64) unless given
+        self.views_per_batch = int(views_per_batch) if views_per_batch else max(1, 4915200 // self.rays_per_view)
         # Renders in flight: `concurrent_batches` view batches x the ensemble members, each with its own
         # working set and stream.  The marching loops are independent, so the narrow, launch-bound tail
         # iterations of one render overlap the wide early iterations of the others.
@@ -104,30 +110,48 @@ class PredictiveInformationScorer:
 
     @torch.no_grad()
     def partial_sums(self, c2w: torch.Tensor, view_traj: torch.Tensor, n_traj: int,
-                     sums: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """c2w [n_views, 3, 4] f32 and view_traj [n_views] i32 ON THE DEVICE -> float64 [n_traj, 4]
-        sums of the per-pixel (rgb, depth, sem, occ) predictive-information terms.  Everything is
-        enqueued on CUDA streams; nothing is read back except the renderers' non-blocking look at
-        their live-ray counters."""
+                     sums: Optional[torch.Tensor] = None, process_group=None) -> torch.Tensor:
+        """c2w [n_views, 3, 4] f32 and view_traj [n_views] i32 ON THE DEVICE, the WHOLE batch on every rank -> float64
+        [n_traj, 4] sums of the per-pixel (rgb, depth, sem, occ) predictive-information terms over the views THIS rank
+        rendered (all of them without torch.distributed; ``schedule`` decides which and in which order: heaviest
+        first).
+        Everything is enqueued on CUDA streams; nothing is read back except the renderers' non-blocking look at their
+        live-ray counters and the cost proxy's [n_views] counts."""
         n_views = c2w.shape[0]
         if sums is None:
             sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
-        vb = self.views_per_batch
+        order, tickets = self.schedule(c2w, process_group)
+        if tickets.store is None:  # local counter: even renderer passes (72 views -> 36 + 36, not 64 + 8)
+            vb = -(-len(order) // max(1, -(-len(order) // self.views_per_batch))) if len(order) else 1
+        else:  # shared counter: about four draws per rank
+            vb = max(1, min(self.views_per_batch, -(-n_views // (4 * tickets.world))))
+        order_dev = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)).to(self.device)
+        self.views_rendered = 0
         self._buffers(min(vb, n_views))
         E, K = len(self.fields), self.concurrent_batches
         with torch.cuda.device(self.device):
             if self._streams is None:
                 self._streams = [[torch.cuda.Stream(device=self.device) for _ in range(E)] for _ in range(K)]
             main = torch.cuda.current_stream()
-            batches = collections.deque((v0, min(n_views, v0 + vb)) for v0 in range(0, n_views, vb))
             free_slots = list(range(K))
-            active = []  # batches in flight: dict(slot, v0, v1, nr, states, gens = [[stream, generator, iterations]])
+            active = []  # batches in flight: dict(slot, views, nr, states, gens = [[stream, generator, iterations]])
+            more = [True]
 
-            def start(v0, v1, slot):
-                nr = (v1 - v0) * self.rays_per_view
+            def draw():
+                """The next batch of view indices (device tensor), or None when the counter has run out."""
+                t = tickets.take(vb)
+                if t >= len(order):
+                    more[0] = False
+                    return None
+                return order_dev[t:min(len(order), t + vb)]
+
+            def start(views, slot):
+                nv = int(views.shape[0])
+                self.views_rendered += nv
+                nr = nv * self.rays_per_view
                 rays_o, rays_d = self._rays[slot][0][:nr], self._rays[slot][1][:nr]
-                call("apnerf_generate_rays", v1 - v0, c2w[v0:v1].contiguous(), self.width, self.height, self.focal,
-                     self.rays_per_view, self.keep_idx, rays_o, rays_d)
+                call("apnerf_generate_rays", nv, c2w.index_select(0, views).contiguous(), self.width, self.height,
+                     self.focal, self.rays_per_view, self.keep_idx, rays_o, rays_d)
                 ready = torch.cuda.Event()
                 ready.record(main)
                 states, gens = [], []
@@ -146,7 +170,7 @@ class PredictiveInformationScorer:
                         gens.append([self._streams[slot][m],
                                      r.render_iter(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
                                                    **self.opts), 0])
-                return dict(slot=slot, v0=v0, v1=v1, nr=nr, states=states, gens=gens)
+                return dict(slot=slot, views=views, nr=nr, states=states, gens=gens)
 
             def finish(job):
                 for stream, _, _ in job["gens"]:
@@ -158,7 +182,7 @@ class PredictiveInformationScorer:
                         self.after_render(r)
                 states = job["states"] + [None] * (4 - len(job["states"]))
                 call("apnerf_score_views", E, states[0], states[1], states[2], states[3], job["nr"], self.rays_per_view,
-                     self.n_sem, view_traj[job["v0"]:job["v1"]].contiguous(), n_traj, sums)
+                     self.n_sem, view_traj.index_select(0, job["views"]).contiguous(), n_traj, sums)
                 free_slots.append(job["slot"])
 
             # Rolling pipeline.  The first dozen marching iterations of a batch are wide, throughput-bound launches; the
@@ -166,11 +190,12 @@ class PredictiveInformationScorer:
             # up to 256 iterations) is a train of small latency-bound launches that leave most of the GPU idle.  A new
             # batch is therefore started, on its own streams, as soon as every batch in flight has left its head phase:
             # the next head's big kernels fill the SMs the tails do not use.
-            while batches or active:
+            while more[0] or active:
                 head_done = all(g[2] >= self.stagger_iters or g[1] is None for job in active for g in job["gens"])
-                if batches and free_slots and (not active or head_done):
-                    v0, v1 = batches.popleft()
-                    active.append(start(v0, v1, free_slots.pop(0)))
+                if more[0] and free_slots and (not active or head_done):
+                    views = draw()
+                    if views is not None:
+                        active.append(start(views, free_slots.pop(0)))
                 for job in list(active):
                     running = False
                     for g in job["gens"]:  # one marching iteration per render, each on its own stream
@@ -206,61 +231,71 @@ class PredictiveInformationScorer:
             if self.n_sem > 0:
                 st[9:, v0:v0 + R] = out[5].t()
 
-    # ---- multi-GPU view assignment ---------------------------------------------------------------------------
+    # ---- scheduling: heavy views first, batches handed out dynamically --------------------------------------------
     @torch.no_grad()
-    def estimate_rows(self, c2w: torch.Tensor) -> torch.Tensor:
-        """Estimated field evaluations per view ([n_views] float32, device): the views are rendered through member 0 at
-        1/64 of their rays (rounded-linspace subsample, the reference's own subsampling rule) and the sample rows
-        the marcher emitted are counted per view.  On the synthetic scene the estimate tracks the full-resolution
-        count to a few per cent while a view's cost varies 3x between poses."""
+    def view_cost_proxy(self, c2w: torch.Tensor) -> np.ndarray:
+        """A cheap, field-free estimate of every view's cost ([n_views] float64, host): 1/64 of the view's rays
+        (rounded-linspace subsample, the reference's own rule) are marched through the occupancy grid for at most 64
+        samples -- ONE launch of the traversal kernel in counting mode -- and the samples are summed per view.  On the
+        synthetic scene it correlates 0.9 with the real number of field evaluations (which varies 8x between poses: a
+        camera inside an occupied region marches from the near plane on), which is all the scheduler needs: the
+        heaviest views must START first, because a view's marching loop is a serial chain of up to 256 iterations that
+        no amount of parallel hardware shortens.  Deterministic, so every rank derives the same order without talking."""
         n_views = c2w.shape[0]
+        est = self.estimators[0]
+        if est.binaries.shape[0] != 1 or n_views == 0:
+            return np.zeros(n_views)
         if self._probe is None:
-            k = int(min(self.rays_per_view, max(256, self.rays_per_view // 64)))
+            k = int(min(self.rays_per_view, max(64, self.rays_per_view // 64)))
             idx = np.round(np.linspace(0, self.rays_per_view - 1, k)).astype(np.int64)
             if self.keep_idx is not None:
                 idx = self.keep_idx.cpu().numpy().astype(np.int64)[idx]
-            self._probe = dict(k=k, keep=torch.from_numpy(idx.astype(np.int32)).to(self.device),
-                               renderer=FusedRenderer(self.device, self.n_sem))
-        pr = self._probe
-        k = pr["k"]
+            self._probe = dict(k=k, keep=torch.from_numpy(idx.astype(np.int32)).to(self.device))
+        k, keep = self._probe["k"], self._probe["keep"]
         n_rays = n_views * k
-        if pr.get("cap", 0) < n_rays:
-            pr["rays_o"] = torch.empty((n_rays, 3), device=self.device)
-            pr["rays_d"] = torch.empty((n_rays, 3), device=self.device)
-            pr["counts"] = torch.empty((2, n_rays), device=self.device, dtype=torch.int32)
-            pr["cap"] = n_rays
-        rays_o, rays_d = pr["rays_o"][:n_rays], pr["rays_d"][:n_rays]
-        counts = pr["counts"].view(-1)[: 2 * n_rays].view(2, n_rays)
-        counts.zero_()
-        with torch.cuda.device(self.device):
-            call("apnerf_generate_rays", n_views, c2w.contiguous(), self.width, self.height, self.focal, k, pr["keep"],
-                 rays_o, rays_d)
-            pr["renderer"].render(self.fields[0], self.estimators[0], rays_o, rays_d, k, probabilistic=False,
-                                  ray_counts=counts, **self.opts)
-        return counts[0].view(n_views, k).sum(1).float() * (self.rays_per_view / k)
+        dev = self.device
+        rays_o, rays_d = torch.empty((n_rays, 3), device=dev), torch.empty((n_rays, 3), device=dev)
+        t0, t1 = torch.empty((n_rays, 1), device=dev), torch.empty((n_rays, 1), device=dev)
+        hits = torch.empty((n_rays, 1), device=dev, dtype=torch.bool)
+        cnt = torch.empty(n_rays, device=dev, dtype=torch.int64)
+        near = torch.full((n_rays,), float(self.opts["near_plane"]), device=dev)
+        far = torch.full((n_rays,), 1e10, device=dev)
+        binaries, aabbs = est.binaries.contiguous(), est.aabbs.contiguous().float()
+        rx, ry, rz = (int(v) for v in binaries.shape[1:])
+        with torch.cuda.device(dev):
+            call("apnerf_generate_rays", n_views, c2w.contiguous(), self.width, self.height, self.focal, k, keep, rays_o,
+                 rays_d)
+            call("apnerf_ray_aabb_intersect", n_rays, rays_o, rays_d, 1, aabbs, float("-inf"), float("inf"), float("inf"),
+                 t0, t1, hits)
+            t_sorted = torch.cat([t0, t1], -1).contiguous()
+            call("apnerf_traverse_grids", n_rays, rays_o, rays_d, None, 1, rx, ry, rz, binaries, aabbs, hits, t_sorted, None,
+                 near, far, float(self.opts["render_step_size"]), float(self.opts["cone_angle"]), 64, 1,
+                 None, None, None, None, None, None, None, None, None, None, cnt, None)
+        return cnt.view(n_views, k).sum(1).double().cpu().numpy()
 
-    def assign_views(self, poses: np.ndarray, rank: int, world: int, process_group=None) -> np.ndarray:
-        """Indices (ascending) of the views this rank renders.  world == 1 or balance == "contiguous": the contiguous
-        balanced slice.  balance == "lpt": every rank estimates the cost of its contiguous slice (``estimate_rows``),
-        the estimates are all-gathered (one small collective) and the views are dealt out longest-processing-time
-        first to the least loaded rank -- the same deterministic assignment on every rank."""
+    def schedule(self, c2w: torch.Tensor, process_group=None):
+        """-> (order, tickets): the view indices this rank may render, in the order they should start (heaviest first by
+        ``view_cost_proxy``), and the counter batches of that order are drawn from -- local for the static splits
+        ("lpt": balanced by the proxy, the default; "contiguous": plain slices), shared through the process group's
+        store for "dynamic" (measured slower on 2 GPUs: the batches get small and the heaviest views queue up)."""
         import torch.distributed as dist
 
-        n = len(poses)
-        lo, hi = shard_range(n, rank, world)
-        if (world == 1 or self.balance == "contiguous" or n < 2 * world
-                or any(e.binaries.shape[0] != 1 for e in self.estimators)):
-            return np.arange(lo, hi)
-        cap = (n + world - 1) // world
-        est = torch.zeros(cap, device=self.device)
-        if hi > lo:
-            c2w = torch.from_numpy(poses_to_c2w(poses[lo:hi])).to(self.device)
-            est[: hi - lo] = self.estimate_rows(c2w)
-        gathered = [torch.empty_like(est) for _ in range(world)]
-        dist.all_gather(gathered, est, group=process_group)
-        g = torch.stack(gathered).cpu().numpy()
-        cost = np.concatenate([g[r, : shard_range(n, r, world)[1] - shard_range(n, r, world)[0]] for r in range(world)])
-        return lpt_assign(cost, world)[rank]
+        n_views = c2w.shape[0]
+        use_dist = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        rank = dist.get_rank(process_group) if use_dist else 0
+        world = dist.get_world_size(process_group) if use_dist else 1
+        self._calls += 1
+        if self.balance == "contiguous":
+            lo, hi = shard_range(n_views, rank, world)
+            return np.arange(lo, hi), _Tickets(hi - lo, None, "")
+        cost = self.view_cost_proxy(c2w)
+        if self.balance == "dynamic" and world > 1:  # batches of the global heavy-first order, drawn from the store
+            store = dist.distributed_c10d._get_default_store()
+            return np.argsort(-cost, kind="stable"), _Tickets(n_views, store, f"apnerf/tickets/{self._uid}/{self._calls}")
+        # "lpt": the views are dealt out longest-processing-time first to the least loaded rank (by the proxy; the same
+        # deterministic split on every rank, no communication); each rank starts its heaviest views first
+        mine = lpt_assign(cost, world)[rank] if world > 1 else np.arange(n_views)
+        return mine[np.argsort(-cost[mine], kind="stable")], _Tickets(len(mine), None, "")
 
     @staticmethod
     def finish(sums: np.ndarray, pixels_per_traj: np.ndarray) -> np.ndarray:
@@ -300,15 +335,13 @@ class PredictiveInformationScorer:
         use_dist = dist.is_available() and dist.is_initialized()
         rank = dist.get_rank(process_group) if use_dist else 0
         world = dist.get_world_size(process_group) if use_dist else 1
-        n_views = poses.shape[0]
-        mine = self.assign_views(poses, rank, world, process_group)
-        c2w_host = torch.from_numpy(poses_to_c2w(poses[mine])).pin_memory()
-        vt_host = torch.from_numpy(np.ascontiguousarray(np.asarray(view_traj)[mine], dtype=np.int32)).pin_memory()
+        c2w_host = torch.from_numpy(poses_to_c2w(poses)).pin_memory()
+        vt_host = torch.from_numpy(np.ascontiguousarray(np.asarray(view_traj), dtype=np.int32)).pin_memory()
         c2w = c2w_host.to(self.device, non_blocking=True)
         vt = vt_host.to(self.device, non_blocking=True)
         sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
-        if len(mine):
-            self.partial_sums(c2w, vt, n_traj, sums)
+        if poses.shape[0]:
+            self.partial_sums(c2w, vt, n_traj, sums, process_group)
         sums = all_reduce_partial_sums(sums, process_group)
         counts = np.bincount(view_traj, minlength=n_traj)[:n_traj] * self.rays_per_view
         host_sums = sums.cpu().numpy()
@@ -340,6 +373,27 @@ def lpt_assign(cost: np.ndarray, world: int):
     return [np.asarray(sorted(b), dtype=np.int64) for b in bins]
 
 
+class _Tickets:
+    """The counter the ranks draw view batches from.  One process: a local integer.  Several ranks: a key of the
+    process group's store (``store.add`` is atomic; one TCP round trip of ~0.1 ms per draw, a handful of draws per rank
+    and call) -- no collective, so a rank never waits for a slower one until the final all-reduce of the sums."""
+
+    def __init__(self, n: int, store, key: str):
+        self.n, self.store, self.key, self.next = n, store, key, 0
+        self.world = 1
+        if store is not None:
+            import torch.distributed as dist
+
+            self.world = dist.get_world_size()
+
+    def take(self, b: int) -> int:
+        """Reserve the next ``b`` positions; returns the first one (>= n when nothing is left)."""
+        if self.store is None:
+            t, self.next = self.next, self.next + b
+            return t
+        return int(self.store.add(self.key, b)) - b
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous, balanced [lo, hi) slice of n units for `rank` of `world`."""
     base, rem = divmod(n, world)
@@ -357,7 +411,7 @@ def probablistic_uncertainty(radiance_fields, estimators, trajectory, *, img_w, 
     if scorer is None:
         scorer = PredictiveInformationScorer(radiance_fields, estimators, img_w, img_h, focal, near_plane=near_plane,
                                              render_step_size=render_step_size, cone_angle=cone_angle,
-                                             alpha_thre=alpha_thre, scale=scale, device=device, views_per_batch=40)
+                                             alpha_thre=alpha_thre, scale=scale, device=device)
         _SCORERS.clear()
         _SCORERS[key] = scorer
     terms = scorer.score_trajectories([np.asarray(trajectory)])[0]

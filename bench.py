@@ -226,12 +226,11 @@ def run_score(args):
     poses_all = synthetic.make_poses(V_total, seed=3)
     view_traj_all = np.minimum(np.arange(V_total) // VIEWS_PER_TRAJ, n_traj - 1).astype(np.int32)
     scorer = apnerf.PredictiveInformationScorer(fields, [est, est], W, H, HFOV_FOCAL, device=dev,
-                                                views_per_batch=args.views_per_batch,
+                                                views_per_batch=args.views_per_batch or None,
                                                 concurrent_batches=args.concurrent_batches,
                                                 balance=args.balance, **OPTS)
-    mine = scorer.assign_views(poses_all, rank, world)  # this rank's view indices (balanced by estimated samples)
-    c2w = torch.from_numpy(apnerf.scoring.poses_to_c2w(poses_all[mine])).to(dev)
-    vt = torch.from_numpy(view_traj_all[mine]).to(dev)
+    c2w = torch.from_numpy(apnerf.scoring.poses_to_c2w(poses_all)).to(dev)  # the whole batch on every rank (12 KB)
+    vt = torch.from_numpy(view_traj_all).to(dev)
     sums = torch.zeros((n_traj, 4), device=dev, dtype=torch.float64)
 
     def barrier():
@@ -265,7 +264,7 @@ def run_score(args):
     sampler.mark_end()
     launches = _lib.kernel_launches()
     ms = e0.elapsed_time(e1)
-    rows_rank = sum(r.rows_evaluated() for r in scorer.all_renderers()) if len(mine) <= args.views_per_batch else None
+    views_mine = scorer.views_rendered  # of the last step (dynamic: varies a little from step to step)
     # end to end through the public API (host poses in, host scores out)
     step_e2e()
     barrier()
@@ -304,12 +303,15 @@ def run_score(args):
                                    f"x 2 ensemble members, 128^3 occ grid, 16-level hash NeRF, sem-num 29, max_samples "
                                    f"1024, render+score (pred-info); {'the same poses sharded' if args.scaling == 'strong' else 'poses per rank fixed'} "
                                    f"over {world} rank(s)",
-                       "views_total": V_total, "views_per_gpu": len(mine), "rays_per_step": rays_per_step, "ensemble": 2,
-                       "n_trajectories": n_traj, "views_per_batch": args.views_per_batch,
+                       "views_total": V_total, "views_per_gpu": views_mine, "rays_per_step": rays_per_step, "ensemble": 2,
+                       "n_trajectories": n_traj, "views_per_batch": scorer.views_per_batch,
                        "poses": "SURVEY 8(d)-3: x,z U(aabb shrunk by 1 m), y 1.5, yaw U[0,2pi), seed 3",
                        "init": f"hash features U(-1,1), Xavier MLPs, density row x{args.density_gain} (BASELINE.md section 6), "
                                f"field seeds {FIELD_SEEDS}",
-                       "density_gain": args.density_gain, "shard": scorer.balance,
+                       "density_gain": args.density_gain,
+                       "shard": {"lpt": "static split balanced by the occupancy-march cost proxy (LPT), heaviest views first",
+                                 "dynamic": "batches drawn heaviest-first from a counter shared by the ranks",
+                                 "contiguous": "contiguous slices"}[scorer.balance],
                        "l2": "per-step working set (> 10 GB at 256 poses) exceeds the 126 MB L2; no flush needed",
                        "mean_samples_per_ray": total_rows / rays_per_step,
                        "parallelism": f"views sharded over {world} rank(s), one all-reduce of [n_traj,4] f64"},
@@ -317,7 +319,7 @@ def run_score(args):
             "per_rank_ms_per_step": {"min": min(per_rank_ms), "max": max(per_rank_ms)},
             "clocks": clocks,
             "e2e": {"value": rays_per_step * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
-                    "h2d_bytes_per_step": int(len(mine) * (12 * 4 + 4)), "d2h_bytes_per_step": int(n_traj * 4 * 8)},
+                    "h2d_bytes_per_step": int(V_total * (12 * 4 + 4)), "d2h_bytes_per_step": int(n_traj * 4 * 8)},
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "scores_sample": np.round(terms[0], 6).tolist(),
         }
@@ -393,7 +395,8 @@ def _train_setup(args, torch, apnerf, synthetic, dev, rank, world):
     ests = [est] + [apnerf.OccGridEstimator(synthetic.ROI_AABB, resolution=128, levels=1).to(dev) for _ in fields[1:]]
     for e in ests[1:]:
         e.load_state_dict(est.state_dict())
-    opts = [torch.optim.Adam(f.parameters(), lr=1e-3, eps=1e-15) for f in fields]  # pipeline.py:173-178
+    # pipeline.py:173-178; fused=True: the same update as one multi-tensor kernel (a PyTorch library op: A18 stays in PyTorch)
+    opts = [torch.optim.Adam(f.parameters(), lr=1e-3, eps=1e-15, fused=True) for f in fields]
     data = synthetic.TrainingSet(n_images=40, width=W, height=H, focal=HFOV_FOCAL, n_classes=N_SEM, seed=4 + rank, device=dev)
     return fields, ests, opts, data
 
@@ -504,7 +507,7 @@ def run_round(args):
     scale = args.round_scale
     Wf, Hf = (640, 640) if scale < 1 else (W, H)  # reference: 640x640 subsampled to 64x64 (scale 0.1); or full 320x240
     scorer = apnerf.PredictiveInformationScorer(fields, ests, Wf, Hf, Wf / 2.0, device=dev, scale=scale,
-                                                views_per_batch=args.views_per_batch, balance=args.balance, **OPTS)
+                                                views_per_batch=args.views_per_batch or None, balance=args.balance, **OPTS)
     trainer = training.EnsembleTrainer(fields, ests, opts, **OPTS)
 
     def one_round(i):
@@ -571,11 +574,12 @@ def main():
     ap.add_argument("--views", type=int, default=256, help="total poses of the batch (strong scaling)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--views-per-gpu", type=int, default=256, help="poses per rank with --scaling weak")
-    ap.add_argument("--views-per-batch", type=int, default=64, help="views rendered per renderer pass")
+    ap.add_argument("--views-per-batch", type=int, default=0, help="views per renderer pass (0: about 5 M rays)")
     ap.add_argument("--concurrent-batches", type=int, default=3,
                     help="view batches rendered concurrently per GPU (each x the ensemble members, own streams)")
-    ap.add_argument("--balance", default="lpt", choices=["lpt", "contiguous"],
-                    help="multi-GPU view assignment: balanced by estimated samples, or contiguous slices")
+    ap.add_argument("--balance", default="lpt", choices=["lpt", "dynamic", "contiguous"],
+                    help="multi-GPU view assignment: static split balanced by the occupancy-march cost proxy (default), "
+                         "batches drawn from a shared counter, or contiguous slices")
     ap.add_argument("--density-gain", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays-per-batch", type=int, default=8192)

@@ -53,6 +53,18 @@ int apnerf_traverse_grids(int n_rays, const float* rays_o, const float* rays_d, 
                           const int64_t* sm_chunk_starts, int64_t* sm_chunk_cnts,
                           float* terminate_planes, void* stream);
 
+/* The samples of OccGridEstimator.sampling (estimators/occ_grid.py:117-131: traverse_grids, then
+ * t_starts = intervals.vals[is_left], t_ends = intervals.vals[is_right], ray_indices = samples.ray_indices) written
+ * directly as packed triples.  Two calls: chunk_starts == NULL counts (chunk_cnts [n_rays] written); then, with
+ * chunk_starts = exclusive scan of the counts, fills ray_indices / t_starts / t_ends.  Same kernel arithmetic as
+ * apnerf_traverse_grids (bit-identical values), without the interval edges and masks. */
+int apnerf_sample_rays(int n_rays, const float* rays_o, const float* rays_d, int n_grids, int rx, int ry, int rz,
+                       const uint8_t* binaries, const float* aabbs, const uint8_t* hits, const float* t_sorted,
+                       const int64_t* t_indices, const float* near_planes, const float* far_planes,
+                       float step_size, float cone_angle, int traverse_steps_limit,
+                       const int64_t* chunk_starts, int64_t* chunk_cnts, int64_t* ray_indices, float* t_starts,
+                       float* t_ends, void* stream);
+
 /* chunk_cnts -> chunk_starts (+ device-side total): RaySegmentsSpec::memalloc_data_from_chunk /
  * compute_chunk_start -- csrc/include/data_spec.hpp:86-106.  scratch: apnerf_scan_scratch_elems(n)
  * int64 elements. */

@@ -152,6 +152,53 @@ def test_gradient_allreduce_world2_rank_without_samples():
         assert np.allclose(wg, 3.0) and np.allclose(bg, 5.0), (rank, wg, bg)  # sum over ranks / 1 contributing rank
 
 
+def test_ticket_counter_hands_out_disjoint_batches():
+    """The scheduler's counter (one process: a local integer; several ranks: an atomic key of the process group's
+    store, exercised by tests/test_multigpu_gpu.py): consecutive draws are disjoint and cover [0, n)."""
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import _Tickets
+
+    t = _Tickets(10, None, "")
+    got = [t.take(4) for _ in range(4)]
+    assert got == [0, 4, 8, 12] and t.world == 1
+
+
+def _ticket_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import _Tickets
+
+    t = _Tickets(64, dist.distributed_c10d._get_default_store(), "apnerf/tickets/test/1")
+    mine = []
+    while True:
+        s = t.take(3)
+        if s >= 64:
+            break
+        mine += list(range(s, min(64, s + 3)))
+    dist.barrier()
+    ret.put((rank, mine, t.world))
+    dist.destroy_process_group()
+
+
+def test_ticket_counter_world2_partitions_the_views():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_ticket_worker, args=(r, 2, port, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [ret.get(timeout=120) for _ in range(2)]
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    views = sorted(got[0][1] + got[1][1])
+    assert views == list(range(64)) and got[0][2] == 2  # disjoint draws that cover every view exactly once
+
+
 def test_lpt_assignment_is_balanced_and_deterministic():
     sys.path.insert(0, ROOT)
     import apnerf

@@ -1,10 +1,10 @@
 """GPU, 2 ranks over NCCL: the view-sharded scorer gives the 1-rank scores (missing #10).
 
-Every rank holds both ensemble members, estimates the cost of its slice of the views, the estimates are
-all-gathered and the views dealt out longest-first (``PredictiveInformationScorer.assign_views``); each rank renders +
-scores its views and ONE all-reduce of [n_traj, 4] float64 sums finishes the job.  Renders are deterministic per view
-and the per-trajectory sums are float64, so the result must match the single-rank one to round-off -- with both the
-balanced ("lpt") and the contiguous shard.  Skipped on a box with one GPU (run it with ``gpurun --gpus 2``)."""
+Every rank holds both ensemble members and the whole pose batch; the views are drawn in batches, heaviest first, from a
+counter in the process group's store (``PredictiveInformationScorer.schedule``), each rank renders + scores what it drew
+and ONE all-reduce of [n_traj, 4] float64 sums finishes the job.  Renders are deterministic per view and the
+per-trajectory sums are float64, so the result must match the single-rank one to round-off -- with the static balanced
+split ("lpt", the default), the shared counter ("dynamic") and the contiguous shard.  Skipped on a box with one GPU (run it with ``gpurun --gpus 2``)."""
 import os
 import socket
 import sys
@@ -44,14 +44,13 @@ def _worker(rank, world, port, balance, ret):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     scorer, poses, traj = _build(dev, balance)
-    mine = scorer.assign_views(poses, rank, world)
     terms = scorer.score_views(poses, traj, 3)
-    ret.put((rank, terms, mine.tolist()))
+    ret.put((rank, terms, scorer.views_rendered))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("balance", ["lpt", "contiguous"])
+@pytest.mark.parametrize("balance", ["lpt", "dynamic", "contiguous"])
 def test_two_rank_scores_equal_one_rank(balance):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -71,9 +70,8 @@ def test_two_rank_scores_equal_one_rank(balance):
     got = sorted([ret.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
     [p.join(timeout=120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    views = sorted(got[0][2] + got[1][2])
-    assert views == list(range(22)), "the ranks' view sets must partition the batch"
+    assert got[0][2] + got[1][2] == 22, "the ranks' draws must partition the batch"
     if balance == "contiguous":
-        assert got[0][2] == list(range(11)) and got[1][2] == list(range(11, 22))
+        assert got[0][2] == 11 and got[1][2] == 11
     for rank, terms, _ in got:
         assert np.abs(terms - ref).max() <= 1e-9, (rank, np.abs(terms - ref).max())
