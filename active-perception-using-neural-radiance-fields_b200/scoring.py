@@ -122,9 +122,12 @@ class PredictiveInformationScorer:
             sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
         order, tickets = self.schedule(c2w, process_group)
         if tickets.store is None:  # local counter: even renderer passes (72 views -> 36 + 36, not 64 + 8)
-            vb = -(-len(order) // max(1, -(-len(order) // self.views_per_batch))) if len(order) else 1
+            n_batches = max(1, -(-len(order) // self.views_per_batch))
         else:  # shared counter: about four draws per rank
-            vb = max(1, min(self.views_per_batch, -(-n_views // (4 * tickets.world))))
+            n_batches = max(1, -(-n_views // max(1, min(self.views_per_batch, -(-n_views // (4 * tickets.world))))))
+        vb = -(-len(order) // n_batches) if len(order) else 1
+        # batch b = every n_batches-th view of the heavy-first order: the heavy views are dealt out over the batches, so
+        # the batches take about equally long and their long tails overlap one another in the rolling pipeline
         order_dev = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)).to(self.device)
         self.views_rendered = 0
         self._buffers(min(vb, n_views))
@@ -139,11 +142,13 @@ class PredictiveInformationScorer:
 
             def draw():
                 """The next batch of view indices (device tensor), or None when the counter has run out."""
-                t = tickets.take(vb)
-                if t >= len(order):
+                b = tickets.take(1)
+                if b >= n_batches or b >= len(order):
                     more[0] = False
                     return None
-                return order_dev[t:min(len(order), t + vb)]
+                if os.environ.get("APNERF_BATCHING", "strided") == "consecutive":
+                    return order_dev[b * vb:(b + 1) * vb].contiguous()
+                return order_dev[b::n_batches].contiguous()
 
             def start(views, slot):
                 nv = int(views.shape[0])
@@ -295,6 +300,8 @@ class PredictiveInformationScorer:
         # "lpt": the views are dealt out longest-processing-time first to the least loaded rank (by the proxy; the same
         # deterministic split on every rank, no communication); each rank starts its heaviest views first
         mine = lpt_assign(cost, world)[rank] if world > 1 else np.arange(n_views)
+        if os.environ.get("APNERF_ORDER", "heavy") == "natural":
+            return mine, _Tickets(len(mine), None, "")
         return mine[np.argsort(-cost[mine], kind="stable")], _Tickets(len(mine), None, "")
 
     @staticmethod

@@ -132,7 +132,7 @@ def _grad_worker_empty_rank(rank, world, port, ret):
         m.bias.grad = torch.full_like(m.bias, 5.0)
     n = allreduce_gradients(m, contributed=(rank == 0))  # rank 1: no gradients at all
     n_none = allreduce_gradients(torch.nn.Linear(2, 2), contributed=False)  # nobody contributed -> 0, zero grads
-    ret.put((rank, n, n_none, m.weight.grad.clone().numpy(), m.bias.grad.clone().numpy()))
+    ret.put((rank, float(n), float(n_none), m.weight.grad.clone().numpy(), m.bias.grad.clone().numpy()))
     dist.destroy_process_group()
 
 
@@ -148,7 +148,7 @@ def test_gradient_allreduce_world2_rank_without_samples():
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     for rank, n, n_none, wg, bg in got:
-        assert n == 1 and n_none == 0
+        assert float(n) == 1 and float(n_none) == 0
         assert np.allclose(wg, 3.0) and np.allclose(bg, 5.0), (rank, wg, bg)  # sum over ranks / 1 contributing rank
 
 
@@ -174,11 +174,12 @@ def _ticket_worker(rank, world, port, ret):
 
     t = _Tickets(64, dist.distributed_c10d._get_default_store(), "apnerf/tickets/test/1")
     mine = []
+    n_batches = 22  # batch b = every 22nd view, as the scorer deals the heavy-first order out
     while True:
-        s = t.take(3)
-        if s >= 64:
+        b = t.take(1)
+        if b >= n_batches:
             break
-        mine += list(range(s, min(64, s + 3)))
+        mine += list(range(64))[b::n_batches]
     dist.barrier()
     ret.put((rank, mine, t.world))
     dist.destroy_process_group()
