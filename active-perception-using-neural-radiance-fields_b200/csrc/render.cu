@@ -25,7 +25,8 @@ namespace apnerf {
 // [8] sample rows evaluated so far in this render (sum of [2] over the finished iterations; 16 ints in all)
 __global__ void render_schedule_kernel(int n_calls, int rays_per_call, int max_samples, int min_samples,
                                        int* __restrict__ n_alive_acc, int* __restrict__ n_samp,
-                                       int* __restrict__ iter_samples, int* __restrict__ counters) {
+                                       int* __restrict__ iter_samples, int* __restrict__ counters,
+                                       int* __restrict__ call_rows) {
   for (int c = threadIdx.x; c < n_calls; c += blockDim.x) {
     const int na = n_alive_acc[c];
     n_alive_acc[c] = 0;
@@ -33,6 +34,7 @@ __global__ void render_schedule_kernel(int n_calls, int rays_per_call, int max_s
     if (iter_samples[c] < max_samples && na > 0) {  // utils.py:896-903
       n = max(min(rays_per_call / na, MAX_ITER_SAMPLES), min_samples);
       iter_samples[c] += n;
+      if (call_rows) call_rows[c] += n * na;
     }
     n_samp[c] = n;
   }
@@ -764,9 +766,10 @@ APNERF_API int apnerf_render_init(int n_rays, int rays_per_call, const float* ra
 }
 
 APNERF_API int apnerf_render_schedule(int n_calls, int rays_per_call, int max_samples, int min_samples,
-                                      int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, void* stream) {
+                                      int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, int* call_rows,
+                                      void* stream) {
   render_schedule_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(n_calls, rays_per_call, max_samples, min_samples,
-                                                             n_alive_acc, n_samp, iter_samples, counters);
+                                                             n_alive_acc, n_samp, iter_samples, counters, call_rows);
   APNERF_CHECK_LAUNCH("render_schedule_kernel");
   return 0;
 }

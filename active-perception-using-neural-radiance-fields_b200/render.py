@@ -19,6 +19,7 @@ Train-mode glue (``render_image_with_occgrid_with_depth_guide``, ``sem_rendering
 utils.py:63-219, 362-461 on top of ``OccGridEstimator.sampling`` and the packed volrend ops.
 """
 import collections
+import time
 from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
@@ -50,6 +51,7 @@ def namedtuple_map(fn, tup):
 class FusedRenderer:
     """Owns the HBM working set of one batch of calls (views x one ensemble member) and
     enqueues the per-iteration kernel sequence schedule -> march -> field -> composite."""
+    host_blocked_s = 0.0  # seconds the enqueuing thread spent waiting for the device (throttle), all renderers: measurement
 
     def __init__(self, device, n_sem: int):
         self.device = torch.device(device)
@@ -111,14 +113,19 @@ class FusedRenderer:
                render_step_size: float = 1e-3, cone_angle: float = 0.0, alpha_thre: float = 0.0,
                early_stop_eps: float = 1e-4, probabilistic: bool = True, state: Optional[Tensor] = None,
                poll_every: int = 4, debug_hook: Optional[Callable] = None, fuse_compositor: bool = False,
-               ray_counts: Optional[Tensor] = None):
+               ray_counts: Optional[Tensor] = None, call_rows: Optional[Tensor] = None,
+               min_samples: Optional[int] = None):
         """Render n_rays = n_calls * rays_per_call rays into the state [9 + C, n_rays] (un-finalised: see
         ``finalize``).  A generator: it enqueues one marching iteration on the CURRENT stream per ``next()``
         and yields the state tensor, so a caller can interleave several renders on different streams.
         The device decides everything; the host only (a) stays at most ~2 * poll_every iterations ahead of
         the GPU and (b) looks at the live-ray counter (pinned memory, copies enqueued every ``poll_every``
         iterations) to stop enqueuing once every ray has terminated.  ``ray_counts`` (int32 [2, n_rays], zeroed
-        by the caller) accumulates per ray the samples evaluated / composited: test instrumentation."""
+        by the caller) accumulates per ray the samples evaluated / composited: test instrumentation.  ``call_rows``
+        (int32 [n_calls], zeroed by the caller) accumulates per call the sample rows sent through the field (the
+        scheduler's cost probe).  ``min_samples`` overrides the reference's lower bound of the per-iteration sample
+        count (1 without a cone angle, else 4; utils.py:894): only the cost probe does that, to finish in fewer,
+        larger iterations -- the composited result is then NOT the reference's."""
         import ctypes
 
         ahead = 2
@@ -130,7 +137,9 @@ class FusedRenderer:
         n_rays = rays_o.shape[0]
         assert n_rays % rays_per_call == 0
         n_calls = n_rays // rays_per_call
-        min_samples = 1 if cone_angle == 0 else 4
+        if min_samples is None:
+            min_samples = 1 if cone_angle == 0 else 4
+        min_samples = int(min_samples)
         # rows of the per-iteration sample list: <= min_samples per ray (utils.py:902); the fused layout
         # pads every warp's run to whole 128-row tiles (<= 2x for the worst non-power-of-two n)
         # + up to 127 padding rows per 32-ray warp; the kernel refuses (flag) rather than overflow
@@ -163,7 +172,7 @@ class FusedRenderer:
             for parity in range(2):
                 cur, nxt = self.alive[(parity + 1) % 2], self.alive[parity % 2]
                 steps = [PreparedCall("apnerf_render_schedule", n_calls, rays_per_call, int(max_samples), min_samples,
-                                      self.n_alive_acc, self.n_samp, self.iter_samples, self.counters)]
+                                      self.n_alive_acc, self.n_samp, self.iter_samples, self.counters, call_rows)]
                 if fuse_compositor:
                     # three launches: tile-aware march -> field + compositor fused -> ordered compaction
                     steps.append(PreparedCall(
@@ -209,7 +218,9 @@ class FusedRenderer:
                     ev.record()
                     events.append((it, ev))
                     if len(events) > ahead:  # throttle: never run more than `ahead` polls ahead of the device
+                        t_wait = time.perf_counter()
                         events[-1 - ahead][1].synchronize()
+                        FusedRenderer.host_blocked_s += time.perf_counter() - t_wait
                     finished = False
                     while events and events[0][1].query():
                         j, _ = events.pop(0)

@@ -11,6 +11,7 @@ per-trajectory partial sums, and ONE all-reduce of [n_traj, 4] float64 finishes 
 """
 import collections
 import os
+import time
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -58,7 +59,7 @@ class PredictiveInformationScorer:
                  height: int, focal: float, *, near_plane: float = 0.1, render_step_size: float = 1e-3,
                  cone_angle: float = 0.004, alpha_thre: float = 0.01, scale: float = 1.0, max_samples: int = 1024,
                  device="cuda:0", views_per_batch: Optional[int] = None, concurrent_batches: int = 3,
-                 balance: str = "lpt"):
+                 balance: str = "dynamic"):
         assert 1 <= len(radiance_fields) <= 4 and len(radiance_fields) == len(estimators)
         self.fields, self.estimators = list(radiance_fields), list(estimators)
         self.width, self.height, self.focal = int(width), int(height), float(focal)
@@ -70,6 +71,7 @@ class PredictiveInformationScorer:
         self.balance = balance
         self.after_render = None  # optional callable(renderer), invoked once per finished render (measurement)
         self._probe = None
+        self.last_probe_ms = 0.0  # wall time of the last cost probe (it ends with the host read of the costs)
         self._calls = 0
         PredictiveInformationScorer._instances += 1
         self._uid = PredictiveInformationScorer._instances  # the same on every rank (scorers are created in lock step)
@@ -92,6 +94,12 @@ class PredictiveInformationScorer:
         self.renderer = self.renderers[0][0]
         self._streams = None
         self.interleave = True  # False: one render after the other on the current stream (measurement)
+        # rays per view of the scheduler's cost probe: 1/768 of the view (100 of 320x240), at least 64
+        self.probe_rays = int(os.environ.get("APNERF_PROBE_RAYS", str(max(64, self.rays_per_view // 768))))
+        self.probe_min_samples = int(os.environ.get("APNERF_PROBE_MIN_SAMPLES", "64"))
+        self.probe_iters = int(os.environ.get("APNERF_PROBE_ITERS", "4"))
+        self.shared_passes_per_rank = int(os.environ.get("APNERF_SHARED_PASSES", "8"))  # "dynamic": passes per rank in the shared counter
+        self.min_batches = int(os.environ.get("APNERF_MIN_BATCHES", "3"))  # renderer passes per rank when view costs are known
         self.stagger_iters = int(os.environ.get("APNERF_STAGGER", "12"))  # a batch leaves its head phase after this many marching iterations (see partial_sums)
         self._states = None
         self._rays = None
@@ -120,17 +128,9 @@ class PredictiveInformationScorer:
         n_views = c2w.shape[0]
         if sums is None:
             sums = torch.zeros((n_traj, 4), device=self.device, dtype=torch.float64)
-        order, tickets = self.schedule(c2w, process_group)
-        if tickets.store is None:  # local counter: even renderer passes (72 views -> 36 + 36, not 64 + 8)
-            n_batches = max(1, -(-len(order) // self.views_per_batch))
-        else:  # shared counter: about four draws per rank
-            n_batches = max(1, -(-n_views // max(1, min(self.views_per_batch, -(-n_views // (4 * tickets.world))))))
-        vb = -(-len(order) // n_batches) if len(order) else 1
-        # batch b = every n_batches-th view of the heavy-first order: the heavy views are dealt out over the batches, so
-        # the batches take about equally long and their long tails overlap one another in the rolling pipeline
-        order_dev = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)).to(self.device)
+        queue = self.schedule(c2w, process_group)
         self.views_rendered = 0
-        self._buffers(min(vb, n_views))
+        self._buffers(min(n_views, queue.max_pass))
         E, K = len(self.fields), self.concurrent_batches
         with torch.cuda.device(self.device):
             if self._streams is None:
@@ -138,17 +138,6 @@ class PredictiveInformationScorer:
             main = torch.cuda.current_stream()
             free_slots = list(range(K))
             active = []  # batches in flight: dict(slot, views, nr, states, gens = [[stream, generator, iterations]])
-            more = [True]
-
-            def draw():
-                """The next batch of view indices (device tensor), or None when the counter has run out."""
-                b = tickets.take(1)
-                if b >= n_batches or b >= len(order):
-                    more[0] = False
-                    return None
-                if os.environ.get("APNERF_BATCHING", "strided") == "consecutive":
-                    return order_dev[b * vb:(b + 1) * vb].contiguous()
-                return order_dev[b::n_batches].contiguous()
 
             def start(views, slot):
                 nv = int(views.shape[0])
@@ -195,10 +184,10 @@ class PredictiveInformationScorer:
             # up to 256 iterations) is a train of small latency-bound launches that leave most of the GPU idle.  A new
             # batch is therefore started, on its own streams, as soon as every batch in flight has left its head phase:
             # the next head's big kernels fill the SMs the tails do not use.
-            while more[0] or active:
+            while queue.has_more() or active:
                 head_done = all(g[2] >= self.stagger_iters or g[1] is None for job in active for g in job["gens"])
-                if more[0] and free_slots and (not active or head_done):
-                    views = draw()
+                if queue.has_more() and free_slots and (not active or head_done):
+                    views = queue.next()
                     if views is not None:
                         active.append(start(views, free_slots.pop(0)))
                 for job in list(active):
@@ -216,6 +205,46 @@ class PredictiveInformationScorer:
                         active.remove(job)
                         finish(job)
         return sums
+
+    def plan_batches(self, order: np.ndarray, cost: Optional[np.ndarray], sharing_ranks: int = 1):
+        """Cut the views this rank may render (``order``) into the renderer passes of the rolling pipeline.
+        Without costs (one GPU, or contiguous slices): even passes of at most ``views_per_batch`` views (72 views ->
+        36 + 36, not 64 + 8), pass b = every n-th view.  With the probe's costs (``order`` is then heaviest first): passes
+        of about EQUAL COST, consecutive in that order, at least ``min_batches`` of them -- so a view that is far heavier
+        than the rest (a camera inside an occupied, transparent region: 20x the median cost, a serial chain of ~110
+        four-sample iterations) gets a pass of its own that starts FIRST, and its long launch-bound tail overlaps the
+        wide kernels of the passes behind it instead of following them (in one pass all views advance in lock step and
+        the tail of the heaviest is exposed at the end).  ``sharing_ranks`` > 1: the passes are drawn from a counter
+        shared by that many ranks ("dynamic"), so there are about ``shared_passes_per_rank`` per rank."""
+        n = len(order)
+        if n == 0:
+            return []
+        if cost is None:
+            n_batches = max(1, -(-n // self.views_per_batch))
+            return [order[b::n_batches] for b in range(n_batches)]
+        want = max(self.min_batches, -(-n // self.views_per_batch),
+                   self.shared_passes_per_rank * sharing_ranks if sharing_ranks > 1 else 1)
+        want = min(want, n)
+        c = np.maximum(np.asarray(cost, dtype=np.float64)[order], 0.0) + 1e-9
+        batches, start, left = [], 0, float(c.sum())
+        for b in range(want):
+            if start >= n:
+                break
+            target = left / (want - b)
+            end, acc = start, 0.0
+            while end < n and end - start < self.views_per_batch and (end == start or acc + 0.5 * c[end] <= target):
+                acc += c[end]
+                end += 1
+            if b == want - 1:  # the last pass takes what is left (further passes follow if it exceeds views_per_batch)
+                end = min(n, start + self.views_per_batch)
+                acc = float(c[start:end].sum())
+            batches.append(order[start:end])
+            left -= acc
+            start = end
+        while start < n:
+            batches.append(order[start:start + self.views_per_batch])
+            start += self.views_per_batch
+        return batches
 
     def _render_unfused(self, field, estimator, rays_o, rays_d, st):
         """Fill the state planes the scorer reads (opacity, variances, semantic logits) from the op-by-op renderer,
@@ -237,52 +266,81 @@ class PredictiveInformationScorer:
                 st[9:, v0:v0 + R] = out[5].t()
 
     # ---- scheduling: heavy views first, batches handed out dynamically --------------------------------------------
+    # ---- scheduling over ranks: a cost probe, then cost-aware passes ------------------------------------------------------
     @torch.no_grad()
     def view_cost_proxy(self, c2w: torch.Tensor) -> np.ndarray:
-        """A cheap, field-free estimate of every view's cost ([n_views] float64, host): 1/64 of the view's rays
-        (rounded-linspace subsample, the reference's own rule) are marched through the occupancy grid for at most 64
-        samples -- ONE launch of the traversal kernel in counting mode -- and the samples are summed per view.  On the
-        synthetic scene it correlates 0.9 with the real number of field evaluations (which varies 8x between poses: a
-        camera inside an occupied region marches from the near plane on), which is all the scheduler needs: the
-        heaviest views must START first, because a view's marching loop is a serial chain of up to 256 iterations that
-        no amount of parallel hardware shortens.  Deterministic, so every rank derives the same order without talking."""
+        """Every view's cost ([n_views] float64, host) from a PROBE RENDER: `probe_rays` rays per view (a rounded-linspace
+        subsample, the reference's own rule) are rendered through every ensemble member with the real renderer -- real
+        occupancy grid, real density field, so rays terminate where the full-resolution ones will -- in a few COARSE
+        marching iterations (`probe_min_samples` = 64 samples per ray and iteration instead of the reference's 4, stopped
+        after `probe_iters` = 4 of them), and the sample rows each view sends through the field are counted on the device
+        (`call_rows` of the schedule kernel); a ray still alive at the cut-off is counted as needing as many samples
+        again.  Field
+        evaluations are what a view costs (the field kernel is half of the step; marcher and compositor scale with the
+        same count) and they vary 40x between poses: a camera inside an occupied but transparent region marches ~440
+        samples per ray from the near plane on, 20x the median view, as a serial chain of ~110 four-sample iterations.
+        Finding THOSE views is what the probe is for (they must start first); the split itself is self-balancing
+        (``schedule``).  The un-truncated probe (min 16 samples, to the end) correlates 0.999 with the full-resolution
+        count (profiles/r02_scaling.md) but is a serial chain of ~60 small launches = 6 ms on every rank; this one is four
+        iterations.  The occupancy-only march count used before could not see transparency at all: the split it produced
+        was WORSE balanced than contiguous slices.  Deterministic (integer counts of deterministic kernels), so every rank
+        computes the same costs without talking."""
         n_views = c2w.shape[0]
-        est = self.estimators[0]
-        if est.binaries.shape[0] != 1 or n_views == 0:
+        if any(e.binaries.shape[0] != 1 for e in self.estimators) or n_views == 0:
             return np.zeros(n_views)
         if self._probe is None:
-            k = int(min(self.rays_per_view, max(64, self.rays_per_view // 64)))
+            k = int(min(self.rays_per_view, max(16, self.probe_rays)))
             idx = np.round(np.linspace(0, self.rays_per_view - 1, k)).astype(np.int64)
             if self.keep_idx is not None:
                 idx = self.keep_idx.cpu().numpy().astype(np.int64)[idx]
-            self._probe = dict(k=k, keep=torch.from_numpy(idx.astype(np.int32)).to(self.device))
+            self._probe = dict(k=k, keep=torch.from_numpy(idx.astype(np.int32)).to(self.device),
+                               renderers=[FusedRenderer(self.device, self.n_sem) for _ in self.fields],
+                               streams=[torch.cuda.Stream(device=self.device) for _ in self.fields])
         k, keep = self._probe["k"], self._probe["keep"]
         n_rays = n_views * k
         dev = self.device
         rays_o, rays_d = torch.empty((n_rays, 3), device=dev), torch.empty((n_rays, 3), device=dev)
-        t0, t1 = torch.empty((n_rays, 1), device=dev), torch.empty((n_rays, 1), device=dev)
-        hits = torch.empty((n_rays, 1), device=dev, dtype=torch.bool)
-        cnt = torch.empty(n_rays, device=dev, dtype=torch.int64)
-        near = torch.full((n_rays,), float(self.opts["near_plane"]), device=dev)
-        far = torch.full((n_rays,), 1e10, device=dev)
-        binaries, aabbs = est.binaries.contiguous(), est.aabbs.contiguous().float()
-        rx, ry, rz = (int(v) for v in binaries.shape[1:])
+        rows = torch.zeros((len(self.fields), n_views), device=dev, dtype=torch.int32)
         with torch.cuda.device(dev):
             call("apnerf_generate_rays", n_views, c2w.contiguous(), self.width, self.height, self.focal, k, keep, rays_o,
                  rays_d)
-            call("apnerf_ray_aabb_intersect", n_rays, rays_o, rays_d, 1, aabbs, float("-inf"), float("inf"), float("inf"),
-                 t0, t1, hits)
-            t_sorted = torch.cat([t0, t1], -1).contiguous()
-            call("apnerf_traverse_grids", n_rays, rays_o, rays_d, None, 1, rx, ry, rz, binaries, aabbs, hits, t_sorted, None,
-                 near, far, float(self.opts["render_step_size"]), float(self.opts["cone_angle"]), 64, 1,
-                 None, None, None, None, None, None, None, None, None, None, cnt, None)
-        return cnt.view(n_views, k).sum(1).double().cpu().numpy()
+            main = torch.cuda.current_stream()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            gens = []
+            for m, (f, e) in enumerate(zip(self.fields, self.estimators)):
+                st = self._probe["streams"][m]
+                st.wait_event(ready)
+                gens.append([st, self._probe["renderers"][m].render_iter(
+                    f, e, rays_o, rays_d, k, probabilistic=False, call_rows=rows[m], min_samples=self.probe_min_samples,
+                    poll_every=0, **self.opts)])
+            for _ in range(self.probe_iters):  # the members' probes advance in lock step on their own streams
+                for g in gens:
+                    if g[1] is not None:
+                        with torch.cuda.stream(g[0]):
+                            if next(g[1], None) is None:
+                                g[1] = None
+            alive = []
+            for m, (st, g) in enumerate(gens):  # abandoned mid-render: n_alive_acc still holds the live rays per view
+                with torch.cuda.stream(st):
+                    alive.append(self._probe["renderers"][m].n_alive_acc[:n_views].clone() if g is not None
+                                 else torch.zeros(n_views, device=dev, dtype=torch.int32))
+                done = torch.cuda.Event()
+                done.record(st)
+                main.wait_event(done)
+            cost = rows.sum(0).double() + torch.stack(alive).sum(0).double() * (self.probe_iters * self.probe_min_samples)
+            return cost.cpu().numpy()
 
     def schedule(self, c2w: torch.Tensor, process_group=None):
-        """-> (order, tickets): the view indices this rank may render, in the order they should start (heaviest first by
-        ``view_cost_proxy``), and the counter batches of that order are drawn from -- local for the static splits
-        ("lpt": balanced by the proxy, the default; "contiguous": plain slices), shared through the process group's
-        store for "dynamic" (measured slower on 2 GPUs: the batches get small and the heaviest views queue up)."""
+        """-> the queue of renderer passes of this rank.  One rank: all views, even passes.  "contiguous": this rank's
+        slice, even passes.  Otherwise the cost probe runs first (``view_cost_proxy``; ~1 ms, the same numbers on every
+        rank) and
+          "dynamic" (default): ALL views are cut into equal-cost passes, heaviest first (`shared_passes_per_rank` per rank),
+             and the ranks draw them from a counter in the process group's store whenever a renderer slot frees up: the
+             heavy views start first on different ranks, and what the cost model cannot see (rows in the long launch-bound
+             tail of a heavy view cost ~1.3x the rows of a wide iteration) is absorbed by who draws next;
+          "lpt": views dealt out longest-processing-time first to the least loaded rank (the same deterministic split on
+             every rank, no communication at all), each rank's share cut into equal-cost passes, heaviest first."""
         import torch.distributed as dist
 
         n_views = c2w.shape[0]
@@ -290,19 +348,26 @@ class PredictiveInformationScorer:
         rank = dist.get_rank(process_group) if use_dist else 0
         world = dist.get_world_size(process_group) if use_dist else 1
         self._calls += 1
-        if self.balance == "contiguous":
+        queue = _PassQueue(self.device)
+        multi_level = any(e.binaries.shape[0] != 1 for e in self.estimators)
+        if world == 1:  # nothing to balance; the order of the passes does not matter on one GPU (measured)
+            queue.add_local(self.plan_batches(np.arange(n_views), None))
+            return queue
+        if self.balance == "contiguous" or n_views < 2 * world or multi_level:
             lo, hi = shard_range(n_views, rank, world)
-            return np.arange(lo, hi), _Tickets(hi - lo, None, "")
+            queue.add_local(self.plan_batches(np.arange(lo, hi), None))
+            return queue
+        t0 = time.perf_counter()
         cost = self.view_cost_proxy(c2w)
-        if self.balance == "dynamic" and world > 1:  # batches of the global heavy-first order, drawn from the store
+        self.last_cost, self.last_probe_ms = cost, 1e3 * (time.perf_counter() - t0)
+        if self.balance == "dynamic":
+            passes = self.plan_batches(np.argsort(-cost, kind="stable"), cost, world)
             store = dist.distributed_c10d._get_default_store()
-            return np.argsort(-cost, kind="stable"), _Tickets(n_views, store, f"apnerf/tickets/{self._uid}/{self._calls}")
-        # "lpt": the views are dealt out longest-processing-time first to the least loaded rank (by the proxy; the same
-        # deterministic split on every rank, no communication); each rank starts its heaviest views first
-        mine = lpt_assign(cost, world)[rank] if world > 1 else np.arange(n_views)
-        if os.environ.get("APNERF_ORDER", "heavy") == "natural":
-            return mine, _Tickets(len(mine), None, "")
-        return mine[np.argsort(-cost[mine], kind="stable")], _Tickets(len(mine), None, "")
+            queue.set_shared(passes, _Tickets(len(passes), store, f"apnerf/tickets/{self._uid}/{self._calls}"))
+            return queue
+        mine = lpt_assign(cost, world)[rank]
+        queue.add_local(self.plan_batches(mine[np.argsort(-cost[mine], kind="stable")], cost))
+        return queue
 
     @staticmethod
     def finish(sums: np.ndarray, pixels_per_traj: np.ndarray) -> np.ndarray:
@@ -367,17 +432,50 @@ def all_reduce_partial_sums(sums: torch.Tensor, process_group=None) -> torch.Ten
     return sums
 
 
-def lpt_assign(cost: np.ndarray, world: int):
-    """Longest-processing-time-first assignment of units with the given costs to `world` bins; returns one ascending
-    index array per bin.  Deterministic (stable sort, ties to the lower bin), so every rank computes the same split."""
+def lpt_assign(cost: np.ndarray, world: int, initial=None):
+    """Longest-processing-time-first assignment of units with the given costs to `world` bins (that already hold the
+    loads `initial`); returns one ascending index array per bin.  Deterministic (stable sort, ties to the lower bin), so
+    every rank computes the same split."""
     order = np.argsort(-np.asarray(cost, dtype=np.float64), kind="stable")
-    load = np.zeros(world)
+    load = np.zeros(world) if initial is None else np.asarray(initial, dtype=np.float64).copy()
     bins = [[] for _ in range(world)]
     for i in order:
         r = int(np.argmin(load))
         bins[r].append(int(i))
         load[r] += max(float(cost[i]), 0.0) + 1e-9
     return [np.asarray(sorted(b), dtype=np.int64) for b in bins]
+
+
+class _PassQueue:
+    """The renderer passes a rank still has to start: its own list, then (once the cost probe has planned them) the
+    passes all ranks share, drawn from the ticket counter."""
+
+    def __init__(self, device):
+        self.device, self.local, self.shared, self.tickets, self.max_pass = device, [], None, None, 1
+
+    def _dev(self, passes):
+        self.max_pass = max([self.max_pass] + [len(b) for b in passes])
+        return [torch.from_numpy(np.ascontiguousarray(b, dtype=np.int64)).to(self.device) for b in passes if len(b)]
+
+    def add_local(self, passes):
+        self.local += self._dev(passes)
+
+    def set_shared(self, passes, tickets):
+        self.shared, self.tickets = self._dev(passes), tickets
+
+    def has_more(self) -> bool:
+        return bool(self.local) or self.shared is not None
+
+    def next(self):
+        """The next pass (device tensor of view indices) or None."""
+        if self.local:
+            return self.local.pop(0)
+        if self.shared is not None:
+            b = self.tickets.take(1)
+            if b < len(self.shared):
+                return self.shared[b]
+            self.shared = None
+        return None
 
 
 class _Tickets:

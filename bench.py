@@ -238,9 +238,15 @@ def run_score(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    own = []  # (start, end-before-the-all-reduce) events of every step: this rank's OWN render + score time
+
     def step_device():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         sums.zero_()
         scorer.partial_sums(c2w, vt, n_traj, sums)
+        b.record()
+        own.append((a, b))
         if world > 1:
             dist.all_reduce(sums)
 
@@ -257,13 +263,19 @@ def run_score(args):
     _lib.LAUNCHES.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    apnerf.FusedRenderer.host_blocked_s = 0.0
+    own.clear()
+    h0 = time.perf_counter()
     for _ in range(args.steps):
         step_device()
+    host_s = time.perf_counter() - h0  # wall time of the enqueuing thread inside the timed steps (no sync in there)
+    host_blocked_s = apnerf.FusedRenderer.host_blocked_s  # ... of which waiting for the device (the renderers' throttle)
     e1.record()
     barrier()
     sampler.mark_end()
     launches = _lib.kernel_launches()
     ms = e0.elapsed_time(e1)
+    own_ms = sum(a.elapsed_time(b) for a, b in own)
     views_mine = scorer.views_rendered  # of the last step (dynamic: varies a little from step to step)
     # end to end through the public API (host poses in, host scores out)
     step_e2e()
@@ -274,13 +286,14 @@ def run_score(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
-    tms = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    tms = torch.tensor([ms, e2e_s * 1e3, 1e3 * (host_s - host_blocked_s), own_ms], device=dev, dtype=torch.float64)
     all_ms = [torch.zeros_like(tms) for _ in range(world)]
     if world > 1:
         dist.all_gather(all_ms, tms)
     else:
         all_ms = [tms]
-    per_rank_ms = [float(t[0]) / args.steps for t in all_ms]
+    per_rank_ms = [float(t[3]) / args.steps for t in all_ms]  # each rank's own work, without the wait in the all-reduce
+    per_rank_host_busy = [float(t[2]) / args.steps for t in all_ms]
     ms, e2e_ms = max(float(t[0]) for t in all_ms), max(float(t[1]) for t in all_ms)
 
     # ---- roofline of the dominant kernel (field_forward_kernel), measured live on every rank ----
@@ -309,14 +322,18 @@ def run_score(args):
                        "init": f"hash features U(-1,1), Xavier MLPs, density row x{args.density_gain} (BASELINE.md section 6), "
                                f"field seeds {FIELD_SEEDS}",
                        "density_gain": args.density_gain,
-                       "shard": {"lpt": "static split balanced by the occupancy-march cost proxy (LPT), heaviest views first",
-                                 "dynamic": "batches drawn heaviest-first from a counter shared by the ranks",
-                                 "contiguous": "contiguous slices"}[scorer.balance],
+                       "shard": {"lpt": "static split balanced by the cost of a low-resolution probe render (LPT), heaviest views first",
+                                 "dynamic": "equal-cost passes drawn heaviest-first from a counter shared by the ranks",
+                                 "contiguous": "contiguous slices"}[scorer.balance] if world > 1 else "one rank: all views",
+                       "schedule_probe_ms": scorer.last_probe_ms,
                        "l2": "per-step working set (> 10 GB at 256 poses) exceeds the 126 MB L2; no flush needed",
                        "mean_samples_per_ray": total_rows / rays_per_step,
                        "parallelism": f"views sharded over {world} rank(s), one all-reduce of [n_traj,4] f64"},
             "samples_per_s": total_rows * args.steps / (ms * 1e-3), "samples_per_step": total_rows,
             "per_rank_ms_per_step": {"min": min(per_rank_ms), "max": max(per_rank_ms)},
+            "host_busy_ms_per_step": {"min": min(per_rank_host_busy), "max": max(per_rank_host_busy),
+                                      "what": "enqueuing thread's wall time inside the timed steps minus its waits for the "
+                                              "device; close to ms_per_step = host-bound"},
             "clocks": clocks,
             "e2e": {"value": rays_per_step * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
                     "h2d_bytes_per_step": int(V_total * (12 * 4 + 4)), "d2h_bytes_per_step": int(n_traj * 4 * 8)},
@@ -577,9 +594,9 @@ def main():
     ap.add_argument("--views-per-batch", type=int, default=0, help="views per renderer pass (0: about 5 M rays)")
     ap.add_argument("--concurrent-batches", type=int, default=3,
                     help="view batches rendered concurrently per GPU (each x the ensemble members, own streams)")
-    ap.add_argument("--balance", default="lpt", choices=["lpt", "dynamic", "contiguous"],
-                    help="multi-GPU view assignment: static split balanced by the occupancy-march cost proxy (default), "
-                         "batches drawn from a shared counter, or contiguous slices")
+    ap.add_argument("--balance", default="dynamic", choices=["lpt", "dynamic", "contiguous"],
+                    help="multi-GPU view assignment: equal-cost passes drawn heaviest-first from a shared counter (default), "
+                         "static split balanced by the probe's costs, or contiguous slices")
     ap.add_argument("--density-gain", type=float, default=6.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rays-per-batch", type=int, default=8192)

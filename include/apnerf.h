@@ -222,9 +222,12 @@ int apnerf_render_init(int n_rays, int rays_per_call, const float* rays_o, const
                        int n_state, float* state, float* t_min, float* t_max, uint8_t* hit, float* near,
                        int* alive, int* n_alive_acc, int* iter_samples, int* total_samples, int n_calls,
                        int* counters, uint32_t* occ_bits, void* stream);
-/* utils.py:896-903: per call n = max(min(R // n_alive, 64), min_samples), iter_samples += n. */
+/* utils.py:896-903: per call n = max(min(R // n_alive, 64), min_samples), iter_samples += n.
+ * call_rows (nullable) int32 [n_calls]: += n * n_alive per call, i.e. the sample rows the call sends through the
+ * field (an upper bound: a ray's last iteration may emit fewer than n) -- the scheduler's per-view cost. */
 int apnerf_render_schedule(int n_calls, int rays_per_call, int max_samples, int min_samples,
-                           int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, void* stream);
+                           int* n_alive_acc, int* n_samp, int* iter_samples, int* counters, int* call_rows,
+                           void* stream);
 /* utils.py:906-929: limited traversal of every live ray from its last terminate plane;
  * emits the compact sample list (s_ray, s_ts, s_te), counters[2] and per-entry (base, count), plus
  * s_x [rows] float4: every sample's midpoint o + d (t_s + t_e) / 2 (utils.py:833-836) normalised by the

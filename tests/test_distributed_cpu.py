@@ -216,3 +216,36 @@ def test_lpt_assignment_is_balanced_and_deterministic():
     again = lpt_assign(cost.copy(), 8)
     assert all(np.array_equal(a, b) for a, b in zip(bins, again))
     assert [len(b) for b in lpt_assign(np.ones(5), 2)] == [3, 2] and lpt_assign(np.zeros(0), 3)[0].size == 0
+
+
+def test_plan_batches_partitions_and_isolates_the_heaviest_view():
+    """The renderer passes of a rank: a partition of its views; without costs even strided passes of at most
+    views_per_batch views; with costs (heaviest-first order) passes of about equal cost, so a view 20x heavier than the
+    median gets the FIRST pass to itself."""
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import PredictiveInformationScorer
+
+    class Stub:  # plan_batches only reads these two attributes
+        views_per_batch, min_batches, shared_passes_per_rank = 64, 3, 8
+
+    plan = lambda order, cost, ranks=1: PredictiveInformationScorer.plan_batches(Stub, np.asarray(order), cost, ranks)
+    even = plan(np.arange(72), None)
+    assert [len(b) for b in even] == [36, 36] and sorted(np.concatenate(even).tolist()) == list(range(72))
+    assert plan(np.arange(0), None) == []
+    rng = np.random.default_rng(2)
+    cost = rng.uniform(1.5, 6.0, 32)
+    cost[7] = 68.0  # the camera inside a transparent box
+    order = np.argsort(-cost, kind="stable")
+    b = plan(order, cost)
+    assert sorted(np.concatenate(b).tolist()) == list(range(32)) and len(b) >= 3
+    assert b[0].tolist() == [7]  # the monster alone, first
+    rest = [cost[x].sum() for x in b[1:]]
+    assert max(rest) / min(rest) < 1.5
+    # many views: never more than views_per_batch per pass
+    cost = rng.uniform(1.0, 2.0, 300)
+    b = plan(np.argsort(-cost, kind="stable"), cost)
+    assert max(len(x) for x in b) <= 64 and sorted(np.concatenate(b).tolist()) == list(range(300))
+    # shared counter: about four passes per rank
+    b = plan(np.argsort(-cost, kind="stable"), cost, 8)
+    assert 64 <= len(b) <= 72 and sorted(np.concatenate(b).tolist()) == list(range(300))

@@ -39,7 +39,7 @@ def hook(pc):
     cnt = None
     if pc.name.startswith("apnerf_field_forward"):
         for rr in scorer.all_renderers():
-            if any(t.data_ptr() == rr.counters[2:3].data_ptr() for t in pc.keep):
+            if hasattr(rr, "counters") and any(t.data_ptr() == rr.counters[2:3].data_ptr() for t in pc.keep):
                 cnt = torch.stack([rr.counters[2], rr.counters[0]]).clone()  # rows this iteration, live rays
     evs.append((pc.name, a0, a1, cnt))
 
@@ -67,7 +67,9 @@ for r, l, ms in rows[: len(rows) // 2]:
     print(f"  {r:9d} {l:8d} {ms:8.3f} {r / ms / 1e6 if ms > 0 else 0:6.2f}")
 for key in ("apnerf_render_march", "apnerf_render_composite"):
     series = [a.elapsed_time(b) for name, a, b, _ in evs if name == key]
-    print(key, "ms per launch, member 0:", " ".join(f"{v:.3f}" for v in series[: len(series) // 2][:24]))
+    half = series[: len(series) // 2]
+    print(key, "ms per launch, member 0 (every 4th launch after the 24th):", " ".join(f"{v:.3f}" for v in half[:24]), "|",
+          " ".join(f"{v:.3f}" for v in half[24::4]))
 scorer.interleave = True
 t0.record()
 for _ in range(5):
