@@ -97,8 +97,13 @@ static int fill_meta(HashGridMeta& m, int n_levels, const uint32_t* meta_host) {
 // Opt-in to > 48 KB of dynamic shared memory once per (kernel instantiation, device): function attributes are
 // per device, and a process may drive several GPUs.
 template <int MODE>
-static int launch_field(const FieldIO& io, const HashGridMeta& m, const FieldConst& fc, int grid, int smem,
+static int launch_field(const FieldIO& io_in, const HashGridMeta& m, const FieldConst& fc, int grid, int smem,
                         cudaStream_t stream, const char* name) {
+  // APNERF_FIELD_PAIR_X=1: x-neighbour pairs through one 16-byte load (field.cuh: ldg_entry_pair).  An experiment
+  // switch, off by default: measured 14 % SLOWER (4.46 vs 5.17 G rows/s, profiles/r02_field_kernel.md).
+  static const int pair_x = getenv("APNERF_FIELD_PAIR_X") ? atoi(getenv("APNERF_FIELD_PAIR_X")) : 0;
+  FieldIO io = io_in;
+  io.pair_x = pair_x;
   static unsigned long long attr_done = 0ull;  // bit d: set on device d
   int dev = 0;
   APNERF_CUDA(cudaGetDevice(&dev));

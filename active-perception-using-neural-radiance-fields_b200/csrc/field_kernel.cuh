@@ -111,6 +111,7 @@ struct FieldIO {
   int* total_samples;           // [n_calls] composited (alpha_thre-visible) samples
   int probabilistic;            // accumulate the variance terms
   int* ray_counts;              // optional [2][n_rays_total]: += samples evaluated / composited per ray (tests)
+  int pair_x;                   // 1: x-neighbour entries through one 16-byte load where they share an aligned pair (ldg_entry_pair)
   int stage_level0;             // 1: copy level 0 of the table (<= 32 KB) into shared memory behind the kernel's own
                                 // regions and gather it from there (launch with FIELD_SMEM_MIN + FIELD_L0_BYTES)
   // --- training forward (kernel instantiation TRAIN): density / rgb get the raw fp16 logits (no exp / sigmoid /
@@ -434,12 +435,13 @@ field_forward_kernel(const FieldIO io, const HashGridMeta meta, const FieldConst
       const int lv[4] = {2 * part, 2 * part + 1, 2 * part + 8, 2 * part + 9};
       uint2 f[4], va[8], vb[8];
       float wa[3], wb[3];
-      gather_level(meta, min(lv[0], nl1), x, io.table, va, wa, part == 0 ? staged_l0 : nullptr);
-      gather_level(meta, min(lv[1], nl1), x, io.table, vb, wb);
+      const bool px = io.pair_x != 0;
+      gather_level(meta, min(lv[0], nl1), x, io.table, va, wa, part == 0 ? staged_l0 : nullptr, px);
+      gather_level(meta, min(lv[1], nl1), x, io.table, vb, wb, nullptr, px);
       f[0] = blend_level(wa, va);
-      gather_level(meta, min(lv[2], nl1), x, io.table, va, wa);
+      gather_level(meta, min(lv[2], nl1), x, io.table, va, wa, nullptr, px);
       f[1] = blend_level(wb, vb);
-      gather_level(meta, min(lv[3], nl1), x, io.table, vb, wb);
+      gather_level(meta, min(lv[3], nl1), x, io.table, vb, wb, nullptr, px);
       f[2] = blend_level(wa, va);
       f[3] = blend_level(wb, vb);
 #pragma unroll
