@@ -135,7 +135,7 @@ class PreparedCall:
     renderer re-launches the same entry points with the same pointers hundreds of times, and the
     ctypes argument marshalling would otherwise cost more than the small kernels themselves."""
 
-    __slots__ = ("name", "fn", "args", "keep")
+    __slots__ = ("name", "fn", "args", "keep", "has_stream")
 
     def __init__(self, name, *args):
         LIB._load()
@@ -153,9 +153,15 @@ class PreparedCall:
                 conv.append(ctypes.c_void_p(0))
             else:
                 conv.append(a)
-        if len(conv) == len(self.fn.argtypes) - 1:
+        self.has_stream = len(conv) == len(self.fn.argtypes) - 1
+        if self.has_stream:
             conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         self.args, self.keep = tuple(conv), keep
+
+    def use_current_stream(self):
+        """Re-target the call at torch's current CUDA stream (the stream is marshalled once, at construction)."""
+        if self.has_stream:
+            self.args = self.args[:-1] + (ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),)
 
     def __call__(self):
         if CALL_HOOK is not None:  # measurement hook (bench.py wraps launches in CUDA events)

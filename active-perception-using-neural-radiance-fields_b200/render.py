@@ -204,6 +204,7 @@ class FusedRenderer:
                         self.n_samp, self.iter_samples, int(max_samples), nxt, self.n_alive_acc, self.total_samples,
                         self.counters, 1 if probabilistic else 0, ray_counts))
                 seq.append(steps)
+            self._seq = seq
             for it in range(max_iters):
                 steps = seq[it % 2]
                 steps[0]()
@@ -230,6 +231,13 @@ class FusedRenderer:
                 yield state
             seq[0][0]()  # one more schedule launch folds the last iteration's rows into counters[8]
         yield state
+
+    def use_current_stream(self) -> None:
+        """Move the REST of the render in flight (``render_iter``) to torch's current CUDA stream: the pre-marshalled
+        per-iteration launches are re-targeted.  The caller orders the two streams (event record / wait)."""
+        for steps in getattr(self, "_seq", ()):
+            for pc in steps:
+                pc.use_current_stream()
 
     def rows_evaluated(self) -> int:
         """Sample rows sent through the field by the last render (host sync)."""

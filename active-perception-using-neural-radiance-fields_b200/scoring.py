@@ -98,8 +98,11 @@ class PredictiveInformationScorer:
         self.probe_rays = int(os.environ.get("APNERF_PROBE_RAYS", str(max(64, self.rays_per_view // 768))))
         self.probe_min_samples = int(os.environ.get("APNERF_PROBE_MIN_SAMPLES", "64"))
         self.probe_iters = int(os.environ.get("APNERF_PROBE_ITERS", "4"))
+        self.probe_tail_factor = float(os.environ.get("APNERF_PROBE_TAIL", "3"))
+        self.throttle = int(os.environ.get("APNERF_DRAW_THROTTLE", "1"))  # "dynamic": a rank ahead of the average load waits
         self.shared_passes_per_rank = int(os.environ.get("APNERF_SHARED_PASSES", "8"))  # "dynamic": passes per rank in the shared counter
         self.min_batches = int(os.environ.get("APNERF_MIN_BATCHES", "3"))  # renderer passes per rank when view costs are known
+        self.tail_priority = int(os.environ.get("APNERF_TAIL_PRIORITY", "0"))  # 1: tails of renders on high-priority streams (measured: no gain)
         self.stagger_iters = int(os.environ.get("APNERF_STAGGER", "12"))  # a batch leaves its head phase after this many marching iterations (see partial_sums)
         self._states = None
         self._rays = None
@@ -135,6 +138,9 @@ class PredictiveInformationScorer:
         with torch.cuda.device(self.device):
             if self._streams is None:
                 self._streams = [[torch.cuda.Stream(device=self.device) for _ in range(E)] for _ in range(K)]
+                # the tail of a render continues on a HIGH-PRIORITY stream (see the rolling pipeline below)
+                self._tail_streams = [[torch.cuda.Stream(device=self.device, priority=-1) for _ in range(E)]
+                                      for _ in range(K)]
             main = torch.cuda.current_stream()
             free_slots = list(range(K))
             active = []  # batches in flight: dict(slot, views, nr, states, gens = [[stream, generator, iterations]])
@@ -163,11 +169,11 @@ class PredictiveInformationScorer:
                         self._streams[slot][m].wait_event(ready)
                         gens.append([self._streams[slot][m],
                                      r.render_iter(f, e, rays_o, rays_d, self.rays_per_view, probabilistic=True, state=st,
-                                                   **self.opts), 0])
+                                                   **self.opts), 0, r, self._tail_streams[slot][m]])
                 return dict(slot=slot, views=views, nr=nr, states=states, gens=gens)
 
             def finish(job):
-                for stream, _, _ in job["gens"]:
+                for stream, *_ in job["gens"]:
                     done = torch.cuda.Event()
                     done.record(stream)
                     main.wait_event(done)
@@ -186,7 +192,7 @@ class PredictiveInformationScorer:
             # the next head's big kernels fill the SMs the tails do not use.
             while queue.has_more() or active:
                 head_done = all(g[2] >= self.stagger_iters or g[1] is None for job in active for g in job["gens"])
-                if queue.has_more() and free_slots and (not active or head_done):
+                if queue.has_more() and free_slots and (not active or head_done) and queue.may_draw(bool(active)):
                     views = queue.next()
                     if views is not None:
                         active.append(start(views, free_slots.pop(0)))
@@ -201,6 +207,18 @@ class PredictiveInformationScorer:
                             else:
                                 g[2] += 1
                                 running = True
+                        if g[1] is not None and g[2] == self.stagger_iters and self.tail_priority:
+                            # The render leaves its head phase: its remaining ~100 iterations are a serial chain of small
+                            # launches -- the critical path of the pass.  They continue on a high-priority stream, so each
+                            # of them waits at most for the kernel that is running, not behind the wide kernels the other
+                            # passes have queued (measured: a rank's 110-iteration view took 58 ms beside other passes and
+                            # 30 ms alone).
+                            hop = torch.cuda.Event()
+                            hop.record(g[0])
+                            g[4].wait_event(hop)
+                            g[0] = g[4]
+                            with torch.cuda.stream(g[0]):
+                                g[3].use_current_stream()
                     if not running:
                         active.remove(job)
                         finish(job)
@@ -274,8 +292,9 @@ class PredictiveInformationScorer:
         occupancy grid, real density field, so rays terminate where the full-resolution ones will -- in a few COARSE
         marching iterations (`probe_min_samples` = 64 samples per ray and iteration instead of the reference's 4, stopped
         after `probe_iters` = 4 of them), and the sample rows each view sends through the field are counted on the device
-        (`call_rows` of the schedule kernel); a ray still alive at the cut-off is counted as needing as many samples
-        again.  Field
+        (`call_rows` of the schedule kernel); a ray still alive at the cut-off is counted as needing `probe_tail_factor`
+        = 3 times as many samples again (such rays sit in transparent occupied space; the heaviest bench view needs
+        880 samples per pixel over both members and the probe then says 1024).  Field
         evaluations are what a view costs (the field kernel is half of the step; marcher and compositor scale with the
         same count) and they vary 40x between poses: a camera inside an occupied but transparent region marches ~440
         samples per ray from the near plane on, 20x the median view, as a serial chain of ~110 four-sample iterations.
@@ -328,7 +347,8 @@ class PredictiveInformationScorer:
                 done = torch.cuda.Event()
                 done.record(st)
                 main.wait_event(done)
-            cost = rows.sum(0).double() + torch.stack(alive).sum(0).double() * (self.probe_iters * self.probe_min_samples)
+            cost = rows.sum(0).double() + torch.stack(alive).sum(0).double() * (
+                self.probe_tail_factor * self.probe_iters * self.probe_min_samples)
             return cost.cpu().numpy()
 
     def schedule(self, c2w: torch.Tensor, process_group=None):
@@ -338,7 +358,12 @@ class PredictiveInformationScorer:
           "dynamic" (default): ALL views are cut into equal-cost passes, heaviest first (`shared_passes_per_rank` per rank),
              and the ranks draw them from a counter in the process group's store whenever a renderer slot frees up: the
              heavy views start first on different ranks, and what the cost model cannot see (rows in the long launch-bound
-             tail of a heavy view cost ~1.3x the rows of a wide iteration) is absorbed by who draws next;
+             tail of a heavy view cost ~1.3x the rows of a wide iteration) is absorbed by who draws next.  A rank whose
+             drawn cost is AHEAD of the average over the ranks (known from the counter: the passes are the same list on
+             every rank) does not draw while it still has a pass in flight (``_PassQueue.may_draw``): kernels of
+             concurrent passes do not overlap on the SMs (the persistent field kernel takes every SM), so a rank that
+             keeps feeding its free slots while it renders a 20x view finishes that view -- and the step -- late
+             (measured on 8 GPUs: every balanced policy ended at the 58 ms of the rank holding that view);
           "lpt": views dealt out longest-processing-time first to the least loaded rank (the same deterministic split on
              every rank, no communication at all), each rank's share cut into equal-cost passes, heaviest first."""
         import torch.distributed as dist
@@ -363,7 +388,8 @@ class PredictiveInformationScorer:
         if self.balance == "dynamic":
             passes = self.plan_batches(np.argsort(-cost, kind="stable"), cost, world)
             store = dist.distributed_c10d._get_default_store()
-            queue.set_shared(passes, _Tickets(len(passes), store, f"apnerf/tickets/{self._uid}/{self._calls}"))
+            queue.set_shared(passes, _Tickets(len(passes), store, f"apnerf/tickets/{self._uid}/{self._calls}"),
+                             [float(cost[b].sum()) for b in passes] if self.throttle else None)
             return queue
         mine = lpt_assign(cost, world)[rank]
         queue.add_local(self.plan_batches(mine[np.argsort(-cost[mine], kind="stable")], cost))
@@ -460,8 +486,36 @@ class _PassQueue:
     def add_local(self, passes):
         self.local += self._dev(passes)
 
-    def set_shared(self, passes, tickets):
+    def set_shared(self, passes, tickets, pass_costs=None):
+        """pass_costs (optional, one per pass, the same on every rank): enables the draw throttle (``may_draw``)."""
+        keep = [i for i, b in enumerate(passes) if len(b)]
         self.shared, self.tickets = self._dev(passes), tickets
+        self.my_load, self._turn, self._blocked, self._heavy = 0.0, 0, False, False
+        self.cum = None
+        if pass_costs is not None and len(keep):
+            c = np.asarray(pass_costs, dtype=np.float64)[keep]
+            mean = float(c.sum()) / len(c)
+            # a pass far above the mean is ONE heavy view (the planner cuts equal-cost passes): its rows sit in a long
+            # launch-bound tail and cost ~1.3x the rows of wide iterations (profiles/r02_scaling.md)
+            c = np.where(c > 2.0 * mean, 1.3 * c, c)
+            self.pass_costs, self.cum, self.slack, self.heavy_above = c, np.concatenate([[0.0], np.cumsum(c)]), mean, 2.0 * mean
+
+    def may_draw(self, has_active: bool, peek_every: int = 6) -> bool:
+        """Draw throttle of the shared queue: a rank that already has a pass in flight draws another one only while the
+        cost it has drawn so far is at most one average pass above the average over the ranks -- and, once it has drawn a
+        HEAVY pass (one view far above the mean), only while it is not above that average at all: the heavy view is the
+        step's critical path and every pass rendered beside it delays it by its whole kernel time.  The average is known
+        without talking to anybody but the counter: passes [0, b) have been drawn, and every rank holds the same list
+        of pass costs.  A rank with nothing in flight always draws, so no rank ever idles and nothing can dead-lock.
+        The counter is looked at (one store round trip) at most every `peek_every` calls."""
+        if self.local or self.shared is None or self.cum is None or not has_active:
+            return True
+        self._turn += 1
+        if self._blocked and self._turn % peek_every:
+            return False
+        b = min(self.tickets.peek(), len(self.shared))
+        self._blocked = self.my_load > self.cum[b] / self.tickets.world + (0.0 if self._heavy else self.slack)
+        return not self._blocked
 
     def has_more(self) -> bool:
         return bool(self.local) or self.shared is not None
@@ -473,6 +527,9 @@ class _PassQueue:
         if self.shared is not None:
             b = self.tickets.take(1)
             if b < len(self.shared):
+                if self.cum is not None:
+                    self.my_load += float(self.pass_costs[b])
+                    self._heavy = self._heavy or self.pass_costs[b] > self.heavy_above
                 return self.shared[b]
             self.shared = None
         return None
@@ -490,6 +547,10 @@ class _Tickets:
             import torch.distributed as dist
 
             self.world = dist.get_world_size()
+
+    def peek(self) -> int:
+        """How many positions have been handed out so far (one store round trip with several ranks)."""
+        return self.next if self.store is None else int(self.store.add(self.key, 0))
 
     def take(self, b: int) -> int:
         """Reserve the next ``b`` positions; returns the first one (>= n when nothing is left)."""

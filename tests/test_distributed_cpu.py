@@ -249,3 +249,32 @@ def test_plan_batches_partitions_and_isolates_the_heaviest_view():
     # shared counter: about four passes per rank
     b = plan(np.argsort(-cost, kind="stable"), cost, 8)
     assert 64 <= len(b) <= 72 and sorted(np.concatenate(b).tolist()) == list(range(300))
+
+
+def test_draw_throttle_holds_back_the_rank_with_the_heavy_pass():
+    """The shared pass queue's throttle: a rank whose drawn cost is ahead of the ranks' average does not draw while it
+    has a pass in flight; with nothing in flight it always draws (no idling, no dead-lock)."""
+    sys.path.insert(0, ROOT)
+    import apnerf
+    from apnerf.scoring import _PassQueue, _Tickets
+
+    class Counter(_Tickets):  # a local counter that pretends to be shared by 4 ranks
+        def __init__(self, n):
+            super().__init__(n, None, "")
+            self.world = 4
+
+    costs = [90.0] + [10.0] * 19
+    q = _PassQueue("cpu")
+    q.set_shared([np.array([i]) for i in range(20)], Counter(20), costs)
+    # the heavy pass (90 > 2 x mean 14) counts 1.3 x 90 = 117 and takes away this rank's slack
+    assert q.may_draw(False) and int(q.next()[0]) == 0 and q.my_load == 117.0
+    assert not q.may_draw(True)  # 117 > 117 / 4
+    q.tickets.next = 12  # the other ranks have drawn passes 1..11 meanwhile: average (117 + 110) / 4 = 57, still behind
+    assert not any(q.may_draw(True) for _ in range(12))
+    q.tickets.next = 20  # everything handed out: average 77 -> still blocked, but nothing is left anyway
+    assert q.may_draw(False)  # nothing in flight: always allowed
+    light = _PassQueue("cpu")
+    light.set_shared([np.array([i]) for i in range(20)], Counter(20), costs)
+    light.tickets.next = 1
+    assert int(light.next()[0]) == 1 and light.my_load == 10.0
+    assert light.may_draw(True)  # 10 <= (117 + 10) / 4 + 14

@@ -92,6 +92,10 @@ def time_shards(shards, label, plan_cost=None, min_batches=3):
 
 contig = [np.arange(*shard_range(V, k, N)) for k in range(N)]
 lpt_probe, lpt_true = lpt_assign(cost, N), lpt_assign(true_rows, N)
+if os.environ.get("PROBE_CHECK_QUICK"):
+    time_shards(lpt_probe, f"LPT(probe) x{N}, one pass")
+    time_shards(lpt_probe, f"LPT(probe) x{N}, equal-cost passes (min 3)", plan_cost=cost, min_batches=3)
+    sys.exit(0)
 time_shards(contig, f"contiguous x{N}, one pass")
 time_shards(lpt_probe, f"LPT(probe) x{N}, one pass")
 for mb in (3, 4, 6):
