@@ -99,6 +99,11 @@ class FusedRenderer:
             self.counters = torch.zeros(16, device=dev, dtype=torch.int32)
             self._tag = 0
 
+    def reserve(self, n_rays: int, n_calls: int, cone_angle: float = 0.004) -> None:
+        """Allocate the working set for renders of up to n_rays rays now (stand-alone compositor layout), so that no
+        render grows it later: a growth in the middle of a step is a cudaMalloc, i.e. a device-wide stall."""
+        self._ensure(int(n_rays), int(n_calls), int(n_rays) * (1 if cone_angle == 0 else 4), need_rows=True)
+
     @torch.no_grad()
     def render(self, *args, **kwargs) -> Tensor:
         """Run ``render_iter`` to completion and return the state (see there)."""

@@ -99,7 +99,10 @@ class PredictiveInformationScorer:
         self.probe_min_samples = int(os.environ.get("APNERF_PROBE_MIN_SAMPLES", "64"))
         self.probe_iters = int(os.environ.get("APNERF_PROBE_ITERS", "4"))
         self.probe_tail_factor = float(os.environ.get("APNERF_PROBE_TAIL", "3"))
-        self.throttle = int(os.environ.get("APNERF_DRAW_THROTTLE", "1"))  # "dynamic": a rank ahead of the average load waits
+        # "dynamic": 1 = a rank ahead of the average drawn cost waits (``_PassQueue.may_draw``).  Off by default: on 8 GPUs
+        # it took the device-timed step from 56.3 to 54.4 ms but the end-to-end call (ranks in lock step after every
+        # call's host read) from 58.3 to 76 ms in the one run there was budget for (profiles/r02_scaling.md)
+        self.throttle = int(os.environ.get("APNERF_DRAW_THROTTLE", "0"))
         self.shared_passes_per_rank = int(os.environ.get("APNERF_SHARED_PASSES", "8"))  # "dynamic": passes per rank in the shared counter
         self.min_batches = int(os.environ.get("APNERF_MIN_BATCHES", "3"))  # renderer passes per rank when view costs are known
         self.tail_priority = int(os.environ.get("APNERF_TAIL_PRIORITY", "0"))  # 1: tails of renders on high-priority streams (measured: no gain)
@@ -134,6 +137,14 @@ class PredictiveInformationScorer:
         queue = self.schedule(c2w, process_group)
         self.views_rendered = 0
         self._buffers(min(n_views, queue.max_pass))
+        # every renderer that can get a pass is sized for the LARGEST pass of the plan now: with passes drawn from the
+        # shared counter a slot may meet its largest pass only steps later, and growing then stalls the device
+        single_level = all(e.binaries.shape[0] == 1 for e in self.estimators)
+        for slot in self.renderers[:max(1, min(self.concurrent_batches, queue.n_passes))]:
+            for r in slot:
+                if single_level:
+                    r.reserve(min(n_views, queue.max_pass) * self.rays_per_view, min(n_views, queue.max_pass),
+                              self.opts["cone_angle"])
         E, K = len(self.fields), self.concurrent_batches
         with torch.cuda.device(self.device):
             if self._streams is None:
@@ -477,10 +488,11 @@ class _PassQueue:
     passes all ranks share, drawn from the ticket counter."""
 
     def __init__(self, device):
-        self.device, self.local, self.shared, self.tickets, self.max_pass = device, [], None, None, 1
+        self.device, self.local, self.shared, self.tickets, self.max_pass, self.n_passes = device, [], None, None, 1, 0
 
     def _dev(self, passes):
         self.max_pass = max([self.max_pass] + [len(b) for b in passes])
+        self.n_passes += sum(1 for b in passes if len(b))
         return [torch.from_numpy(np.ascontiguousarray(b, dtype=np.int64)).to(self.device) for b in passes if len(b)]
 
     def add_local(self, passes):
