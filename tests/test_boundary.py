@@ -101,3 +101,34 @@ def test_view_selection_matches_reference_indexing_for_short_trajectories():
         ref = traj[np.hstack((a, b)).astype(int)]
         got = traj[uncertainty_view_indices(n)]
         assert got.shape == (40, 7) and np.array_equal(got, ref)
+
+
+def _cuobjdump(*args):
+    import shutil
+    import subprocess
+
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    return subprocess.run([exe, *args], capture_output=True, text=True, check=True).stdout
+
+
+def test_built_kernels_match_the_documented_design(apnerf):
+    """The shipped libapnerf.so is an sm_100a build whose hot kernels have the register budgets DESIGN.md argues
+    from, and whose field / backward / weight-gradient kernels really are tcgen05 + TMEM code (UTCHMMA = tcgen05.mma,
+    LDTM / STTM = tcgen05.ld / st, UTCBAR = tcgen05.commit): a recompiled mma.sync kernel would not contain them."""
+    import re
+
+    usage = _cuobjdump("-res-usage", apnerf._lib.LIB_PATH)
+    assert "sm_100a" in usage
+    regs = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+)", usage):
+        regs[m.group(1)] = int(m.group(2))
+    pick = lambda frag: [v for k, v in regs.items() if frag in k]
+    assert pick("field_forward_kernel") and max(pick("field_forward_kernel")) <= 72  # 832 threads x 72 <= 65 536
+    assert max(pick("render_composite_kernel")) <= 64  # 8 CTAs of 128 threads per SM
+    assert max(v for k, v in regs.items() if "render_march_kernel" in k) <= 64  # 4 CTAs of 256 threads per SM
+    assert max(pick("field_wgrad_kernel")) <= 64 and max(pick("field_backward_kernel")) <= 80
+    sass = _cuobjdump("-sass", apnerf._lib.LIB_PATH)
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTCBAR"):
+        assert sass.count(mnemonic) > 0, f"no {mnemonic} in the shipped SASS: the tcgen05 path is missing"
