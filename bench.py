@@ -180,17 +180,19 @@ def run_reference(args):
     if rank != 0:
         return
     cp = CpuPath(args.density_gain)
-    times, rays = [], 0
+    times, rays, comp = [], 0, 0
     for i in range(args.warmup + args.steps):
-        r, _, dt = cp.view(i)
+        r, ns, dt = cp.view(i)
         if i >= args.warmup:
             times.append(dt)
             rays += r
+            comp += ns
     total = sum(times)
     v = rays / total
     cb = dict(value=v, unit="rays/s", cores=int(cp.O.N_THREADS), kind="port",
               sample=f"each step: one whole 320x240 view of the bench's pose set x 2 members (153 600 rays) + scoring; "
-                     f"{args.steps} timed steps, {total:.1f} s")
+                     f"views {args.warmup}..{args.warmup + args.steps - 1}, {comp / max(1, rays):.1f} composited samples "
+                     f"per ray; {args.steps} timed steps, {total:.1f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
