@@ -175,6 +175,22 @@ def cpu_baseline(density_gain, n_views=1):
                        f"cores (the reference's own CUDA/tcnn path has no CPU implementation)")
 
 
+def _score_static_config(args, world):
+    """The part of `config` that names the workload (identical for the GPU arm and the reference arm)."""
+    V_total = args.views if args.scaling == "strong" else args.views_per_gpu * world
+    return {"workload": f"planner candidate-view batch (BASELINE.json configs[2]): {V_total} poses x {W}x{H} rays "
+                        f"x 2 ensemble members, 128^3 occ grid, 16-level hash NeRF, sem-num 29, max_samples "
+                        f"1024, render+score (pred-info); {'the same poses sharded' if args.scaling == 'strong' else 'poses per rank fixed'} "
+                        f"over {world} rank(s)",
+            "views_total": V_total, "rays_per_step": V_total * W * H * len(FIELD_SEEDS), "ensemble": len(FIELD_SEEDS),
+            "n_trajectories": max(1, V_total // VIEWS_PER_TRAJ),
+            "poses": "SURVEY 8(d)-3: x,z U(aabb shrunk by 1 m), y 1.5, yaw U[0,2pi), seed 3",
+            "init": f"hash features U(-1,1), Xavier MLPs, density row x{args.density_gain} (BASELINE.md section 6), "
+                    f"field seeds {FIELD_SEEDS}",
+            "density_gain": args.density_gain,
+            "l2": "per-step working set (> 10 GB at 256 poses) exceeds the 126 MB L2; no flush needed"}
+
+
 def run_reference(args):
     rank, _, _ = _dist_env()
     if rank != 0:
@@ -198,9 +214,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32 (fp16-rounded MLP operands) / f64 scoring",
         "data": "synthetic",
-        "config": {"workload": "planner candidate-view batch (BASELINE.json configs[2]), bounded CPU sample per step: "
-                               "1 whole 320x240 view x 2 members of the same 256-pose set",
-                   "rays_per_step": rays // max(1, args.steps), "density_gain": args.density_gain},
+        "config": dict(_score_static_config(args, max(1, args.gpus)),
+                       sample="bounded CPU sample per step: 1 whole 320x240 view x 2 members of the workload's pose set",
+                       sample_rays_per_step=rays // max(1, args.steps)),
         "cpu_baseline": cb, "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -314,23 +330,14 @@ def run_score(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f16 MLP operands / f32 accumulate+compositing / f64 scoring", "data": "synthetic",
-            "config": {"workload": f"planner candidate-view batch (BASELINE.json configs[2]): {V_total} poses x {W}x{H} rays "
-                                   f"x 2 ensemble members, 128^3 occ grid, 16-level hash NeRF, sem-num 29, max_samples "
-                                   f"1024, render+score (pred-info); {'the same poses sharded' if args.scaling == 'strong' else 'poses per rank fixed'} "
-                                   f"over {world} rank(s)",
-                       "views_total": V_total, "views_per_gpu": views_mine, "rays_per_step": rays_per_step, "ensemble": 2,
-                       "n_trajectories": n_traj, "views_per_batch": scorer.views_per_batch,
-                       "poses": "SURVEY 8(d)-3: x,z U(aabb shrunk by 1 m), y 1.5, yaw U[0,2pi), seed 3",
-                       "init": f"hash features U(-1,1), Xavier MLPs, density row x{args.density_gain} (BASELINE.md section 6), "
-                               f"field seeds {FIELD_SEEDS}",
-                       "density_gain": args.density_gain,
+            "config": dict(_score_static_config(args, world), **{
+                       "views_per_gpu": views_mine, "views_per_batch": scorer.views_per_batch,
                        "shard": {"lpt": "static split balanced by the cost of a low-resolution probe render (LPT), heaviest views first",
                                  "dynamic": "equal-cost passes drawn heaviest-first from a counter shared by the ranks",
                                  "contiguous": "contiguous slices"}[scorer.balance] if world > 1 else "one rank: all views",
                        "schedule_probe_ms": scorer.last_probe_ms,
-                       "l2": "per-step working set (> 10 GB at 256 poses) exceeds the 126 MB L2; no flush needed",
                        "mean_samples_per_ray": total_rows / rays_per_step,
-                       "parallelism": f"views sharded over {world} rank(s), one all-reduce of [n_traj,4] f64"},
+                       "parallelism": f"views sharded over {world} rank(s), one all-reduce of [n_traj,4] f64"}),
             "samples_per_s": total_rows * args.steps / (ms * 1e-3), "samples_per_step": total_rows,
             "per_rank_ms_per_step": {"min": min(per_rank_ms), "max": max(per_rank_ms)},
             "host_busy_ms_per_step": {"min": min(per_rank_host_busy), "max": max(per_rank_host_busy),
